@@ -1,0 +1,149 @@
+// nb_common.cuh -- shared device/host helpers for the sm_100a direct-sum gravity kernels.
+//
+// Everything here is written for Blackwell B200 (sm_100a) only: packed f32x2
+// arithmetic (FFMA2/FADD2/FMUL2), 1-D bulk TMA copies completed on mbarriers,
+// MUFU.RSQ / MUFU.RSQ64H seeds.  There is no other code path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nbody_b200.h"
+
+namespace nb {
+
+constexpr double kG = NB_G;  // reference: src/hpc/nbody.py:18
+
+// Bodies are streamed through shared memory in chunks of this many bodies.  Every
+// j-segment, tile and padded system length is a multiple of it, so the unrolled
+// inner loops never need a remainder and every bulk copy is a multiple of 16 B.
+constexpr int kChunkBodies = NB_CHUNK_BODIES;
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (C ABI: return codes + a thread-local message, never exceptions)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define NB_CUDA_OK(expr)                                    \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) return nb::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define NB_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            nb::set_error(__VA_ARGS__);       \
+            return NB_ERR_INVALID;            \
+        }                                     \
+    } while (0)
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return NB_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// --- mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP) -------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    // make the initialised barriers visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// --- fp32 ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.RSQ, no denormal fix-up code
+    return y;
+}
+
+// --- fp64 ----------------------------------------------------------------------------------------
+// MUFU.RSQ64H seed (about 2^-22 relative).  Callers refine it; see pair_f64().
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// One softened pair interaction in fp64, accumulating into (ax, ay, az).
+//   reference: src/hpc/nbody.py:47-60   r2 = dx^2+dy^2+dz^2+eps^2; factor = G*m_j / (sqrt(r2)*r2)
+// gm_j = G*m_j is folded on the host side of the kernel.  factor = gm * r2^(-3/2) is formed as
+//   y0 = seed(r2),  e = 1 - r2*y0^2,  r2^(-3/2) = y0^3 * (1 + 3/2 e + 15/8 e^2 + O(e^3)),
+// i.e. one third-order correction of the cubed seed: truncation 35/16 e^3 < 2^-64 for |e| < 2^-21.
+// 17 FP64-pipe operations + 1 MUFU per interaction.
+template <bool kZeroEps>
+__device__ __forceinline__ void pair_f64(double xi, double yi, double zi, double xj, double yj, double zj, double gmj,
+                                         double eps2, double& ax, double& ay, double& az) {
+    const double dx = xj - xi;
+    const double dy = yj - yi;
+    const double dz = zj - zi;
+    double r2 = fma(dx, dx, eps2);
+    r2 = fma(dy, dy, r2);
+    r2 = fma(dz, dz, r2);
+    double y0 = rsqrt_seed(r2);
+    if (kZeroEps) y0 = (r2 > 0.0) ? y0 : 0.0;  // eps == 0: the i == j term (and exact overlaps) contribute 0
+    const double t = r2 * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double y2 = y0 * y0;
+    const double g = gmj * y0;
+    const double w = y2 * g;
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    const double f = fma(w, q, w);
+    ax = fma(f, dx, ax);
+    ay = fma(f, dy, ay);
+    az = fma(f, dz, az);
+}
+
+// NumPy-order leapfrog arithmetic: every product and sum rounded once, never contracted,
+// as in  v += 0.5*dt*a ; x += dt*v  (src/hpc/nbody.py:205,208,214).
+__device__ __forceinline__ double mul_add_unfused(double a, double b, double c) {
+    return __dadd_rn(c, __dmul_rn(a, b));
+}
+__device__ __forceinline__ float mul_add_unfused(float a, float b, float c) { return __fadd_rn(c, __fmul_rn(a, b)); }
+
+#endif  // __CUDACC__
+
+}  // namespace nb

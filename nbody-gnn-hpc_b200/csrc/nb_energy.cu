@@ -1,0 +1,116 @@
+// nb_energy.cu -- K4: kinetic and potential energy of a slab of bodies, float64 throughout (sm_100a).
+//
+// Replaces compute_total_energy, reference src/hpc/nbody.py:101-130 (single-threaded there) and the
+// per-step energy of src/utils/metrics.py:62-109 (O(N^2) memory there).
+//   K = sum_i 1/2 m_i |v_i|^2                                   nbody.py:116-118
+//   U = - sum_{i<j} G m_i m_j / sqrt(r_ij^2 + eps^2)             nbody.py:122-128
+// evaluated as U = -1/2 sum_i m_i sum_{j != i} G m_j / sqrt(...) so that rows [i0, i0+n_i) can be
+// owned by one rank; ranks add their (K, U).  Reduction order is fixed: thread-sequential over j,
+// warp shuffle tree, warp partials in warp order, block partials in block order.
+#include "nb_common.cuh"
+
+namespace nb {
+
+constexpr int kEnergyBlock = 128;
+constexpr int kEnergyTile = 128;
+
+__device__ __forceinline__ double rsqrt_f64(double r2) {
+    const double y0 = rsqrt_seed(r2);
+    const double e = fma(-(r2 * y0), y0, 1.0);
+    return fma(y0, e * fma(0.375, e, 0.5), y0);  // y0 * (1 + e/2 + 3/8 e^2)
+}
+
+__global__ void __launch_bounds__(kEnergyBlock)
+energy_kernel(const double* __restrict__ pos, const double* __restrict__ vel, const void* __restrict__ masses,
+              int masses_are_f32, int n, int i0, int n_i, double eps2, double* __restrict__ block_ku) {
+    __shared__ double4 tile[kEnergyTile];
+    __shared__ double warp_k[kEnergyBlock / 32], warp_u[kEnergyBlock / 32];
+    const int li = blockIdx.x * kEnergyBlock + threadIdx.x;
+    const bool valid = li < n_i;
+    const int gi = i0 + (valid ? li : 0);
+    auto mass = [&](int idx) {
+        return masses_are_f32 ? (double)static_cast<const float*>(masses)[idx] : static_cast<const double*>(masses)[idx];
+    };
+    const double xi = pos[(size_t)gi * 3 + 0], yi = pos[(size_t)gi * 3 + 1], zi = pos[(size_t)gi * 3 + 2];
+    double phi = 0.0;
+    for (int j0 = 0; j0 < n; j0 += kEnergyTile) {
+        const int j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < n) tile[threadIdx.x] = make_double4(pos[(size_t)j * 3], pos[(size_t)j * 3 + 1], pos[(size_t)j * 3 + 2], kG * mass(j));
+        else tile[threadIdx.x] = make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncthreads();
+        const int cnt = min(kEnergyTile, n - j0);
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const double4 p = tile[t];
+            const double dx = p.x - xi, dy = p.y - yi, dz = p.z - zi;
+            const double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
+            const double term = p.w * rsqrt_f64(r2);
+            phi += (j0 + t != gi && r2 > 0.0) ? term : 0.0;
+        }
+    }
+    double k = 0.0, u = 0.0;
+    if (valid) {
+        const double m = mass(gi);
+        const double vx = vel[(size_t)gi * 3 + 0], vy = vel[(size_t)gi * 3 + 1], vz = vel[(size_t)gi * 3 + 2];
+        k = 0.5 * m * (vx * vx + vy * vy + vz * vz);
+        u = -0.5 * m * phi;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        k += __shfl_down_sync(0xffffffffu, k, off);
+        u += __shfl_down_sync(0xffffffffu, u, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        warp_k[threadIdx.x >> 5] = k;
+        warp_u[threadIdx.x >> 5] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bk = 0.0, bu = 0.0;
+        for (int w = 0; w < kEnergyBlock / 32; ++w) {
+            bk += warp_k[w];
+            bu += warp_u[w];
+        }
+        block_ku[2 * blockIdx.x + 0] = bk;
+        block_ku[2 * blockIdx.x + 1] = bu;
+    }
+}
+
+__global__ void energy_final_kernel(const double* __restrict__ block_ku, int n_blocks, double* __restrict__ out_ku) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double k = 0.0, u = 0.0;
+        for (int b = 0; b < n_blocks; ++b) {
+            k += block_ku[2 * b];
+            u += block_ku[2 * b + 1];
+        }
+        out_ku[0] = k;
+        out_ku[1] = u;
+    }
+}
+
+}  // namespace nb
+
+extern "C" {
+
+size_t nb_energy_workspace_bytes(int n, int n_i) {
+    (void)n;
+    const size_t blocks = (size_t)nb::ceil_div(n_i > 0 ? n_i : 1, nb::kEnergyBlock);
+    return (blocks * 2 * sizeof(double) + 255) / 256 * 256;
+}
+
+int nb_energy_f64(const double* pos, const double* vel, const void* masses, int masses_are_f32, int n, int i0, int n_i,
+                  double softening, double* out_ku, void* ws, size_t ws_bytes, nb_stream_t s) {
+    NB_REQUIRE(pos && vel && masses && out_ku && ws, "null pointer argument");
+    NB_REQUIRE(n > 0 && i0 >= 0 && n_i > 0 && i0 + n_i <= n, "slab [%d, %d) outside system of %d bodies", i0, i0 + n_i, n);
+    NB_REQUIRE(ws_bytes >= nb_energy_workspace_bytes(n, n_i), "energy workspace too small");
+    const int blocks = nb::ceil_div(n_i, nb::kEnergyBlock);
+    cudaStream_t st = (cudaStream_t)s;
+    nb::energy_kernel<<<blocks, nb::kEnergyBlock, 0, st>>>(pos, vel, masses, masses_are_f32, n, i0, n_i,
+                                                           softening * softening, static_cast<double*>(ws));
+    if (int rc = nb::check_launch("energy kernel")) return rc;
+    nb::energy_final_kernel<<<1, 32, 0, st>>>(static_cast<const double*>(ws), blocks, out_ku);
+    return nb::check_launch("energy final kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,537 @@
+// nb_force.cu -- K1 (tiled i-j force) and K2 (force pass fused with the leapfrog) for one
+// system held in stream layout, float32 and float64, for sm_100a.
+//
+// Replaces compute_accelerations_direct (reference src/hpc/nbody.py:22-66) and
+// NBodySimulator.step / the loop of run (src/hpc/nbody.py:202-218, 237-241).
+//
+// Decomposition.  grid = (i-tiles, j-segments).  A CTA owns kBlock*kP bodies i (kP per thread, in
+// registers) and one j-segment; the segment is streamed global -> shared memory as 4 KB tiles by
+// 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier, 4-deep ring), every thread reads
+// each j (pair) with broadcast LDS.128 and applies it to its kP bodies.  Segment partials go to
+// the workspace; nb_finish_* adds them in ascending segment order and, for K2, applies the
+// closing kick, writes the snapshot, applies the next opening kick and drift, and writes the new
+// positions into the other stream buffer -- positions never leave HBM between steps.
+//
+// float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
+// (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
+// float64 inner loop: pair_f64() in nb_common.cuh, 17 FP64-pipe operations + 1 MUFU.RSQ64H.
+#include "nb_common.cuh"
+
+namespace nb {
+
+constexpr int kStages = 4;
+constexpr int kTileBytes = 4096;
+
+// Stream the byte range [src, src + total_bytes) through the shared-memory ring, calling
+// consume(tile_ptr, tile_bytes) on every tile by all threads of the CTA.
+template <class Consume>
+__device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int total_bytes, char* ring,
+                                             uint64_t* bars, Consume&& consume) {
+    const int n_tiles = (total_bytes + kTileBytes - 1) / kTileBytes;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < kStages && t < n_tiles; ++t) {
+            const int bytes = min(kTileBytes, total_bytes - t * kTileBytes);
+            mbar_arrive_expect_tx(&bars[t], bytes);
+            tma_load_1d(ring + t * kTileBytes, src + (size_t)t * kTileBytes, bytes, &bars[t]);
+        }
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+        const int slot = t % kStages;
+        mbar_wait(&bars[slot], (t / kStages) & 1);
+        const int bytes = min(kTileBytes, total_bytes - t * kTileBytes);
+        consume(ring + slot * kTileBytes, bytes);
+        __syncthreads();  // every thread is done with this slot before it is refilled
+        const int nt = t + kStages;
+        if (threadIdx.x == 0 && nt < n_tiles) {
+            const int nbytes = min(kTileBytes, total_bytes - nt * kTileBytes);
+            mbar_arrive_expect_tx(&bars[slot], nbytes);
+            tma_load_1d(ring + slot * kTileBytes, src + (size_t)nt * kTileBytes, nbytes, &bars[slot]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// float32 force kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stream, int body, int c) {
+    return stream[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
+}
+
+template <int kP, int kBlock, bool kZeroEps>
+__global__ void __launch_bounds__(kBlock)
+force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, float eps2,
+                 float* __restrict__ partial) {
+    __shared__ __align__(128) char ring[kStages * kTileBytes];
+    __shared__ __align__(8) uint64_t bars[kStages];
+
+    const int seg = blockIdx.y;
+    const int j0 = seg * seg_len;
+    const int j1 = min(j0 + seg_len, n_pad);
+    const int li0 = blockIdx.x * (kBlock * kP) + threadIdx.x;
+
+    float xi[kP], yi[kP], zi[kP];
+    float2 ax[kP], ay[kP], az[kP];
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+        const int gi = i0 + min(li0 + k * kBlock, n_i - 1);
+        xi[k] = f32_stream_coord(stream, gi, 0);
+        yi[k] = f32_stream_coord(stream, gi, 1);
+        zi[k] = f32_stream_coord(stream, gi, 2);
+        ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
+    }
+    const float2 e2 = make_float2(eps2, eps2);
+
+    auto consume = [&](const char* tile, int bytes) {
+        const float4* __restrict__ t = reinterpret_cast<const float4*>(tile);
+        const int n_pairs = bytes >> 5;
+#pragma unroll 4
+        for (int jp = 0; jp < n_pairs; ++jp) {
+            const float4 A = t[2 * jp];      // x0 x1 y0 y1
+            const float4 B = t[2 * jp + 1];  // z0 z1 gm0 gm1
+            const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
+            const float2 zj = make_float2(B.x, B.y), gj = make_float2(B.z, B.w);
+#pragma unroll
+            for (int k = 0; k < kP; ++k) {
+                const float2 dx = __fadd2_rn(xj, make_float2(-xi[k], -xi[k]));
+                const float2 dy = __fadd2_rn(yj, make_float2(-yi[k], -yi[k]));
+                const float2 dz = __fadd2_rn(zj, make_float2(-zi[k], -zi[k]));
+                float2 r2 = __ffma2_rn(dx, dx, e2);
+                r2 = __ffma2_rn(dy, dy, r2);
+                r2 = __ffma2_rn(dz, dz, r2);
+                float2 inv;
+                inv.x = rsqrt_approx(r2.x);
+                inv.y = rsqrt_approx(r2.y);
+                if (kZeroEps) {
+                    inv.x = (r2.x > 0.f) ? inv.x : 0.f;
+                    inv.y = (r2.y > 0.f) ? inv.y : 0.f;
+                }
+                const float2 inv2 = __fmul2_rn(inv, inv);
+                float2 f = __fmul2_rn(gj, inv);
+                f = __fmul2_rn(f, inv2);
+                ax[k] = __ffma2_rn(f, dx, ax[k]);
+                ay[k] = __ffma2_rn(f, dy, ay[k]);
+                az[k] = __ffma2_rn(f, dz, az[k]);
+            }
+        }
+    };
+    stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 16, (j1 - j0) * 16, ring, bars, consume);
+
+    float* __restrict__ out = partial + (size_t)seg * 3 * n_i;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+        const int li = li0 + k * kBlock;
+        if (li < n_i) {
+            out[li] = ax[k].x + ax[k].y;  // even-j lane + odd-j lane
+            out[(size_t)n_i + li] = ay[k].x + ay[k].y;
+            out[(size_t)2 * n_i + li] = az[k].x + az[k].y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// float64 force kernel
+// ------------------------------------------------------------------------------------------------
+template <int kP, int kBlock, bool kZeroEps>
+__global__ void __launch_bounds__(kBlock)
+force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, double eps2,
+                 double* __restrict__ partial) {
+    __shared__ __align__(128) char ring[kStages * kTileBytes];
+    __shared__ __align__(8) uint64_t bars[kStages];
+
+    const int seg = blockIdx.y;
+    const int j0 = seg * seg_len;
+    const int j1 = min(j0 + seg_len, n_pad);
+    const int li0 = blockIdx.x * (kBlock * kP) + threadIdx.x;
+
+    double xi[kP], yi[kP], zi[kP], ax[kP], ay[kP], az[kP];
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+        const int gi = i0 + min(li0 + k * kBlock, n_i - 1);
+        const double4 q = reinterpret_cast<const double4*>(stream)[gi];
+        xi[k] = q.x;
+        yi[k] = q.y;
+        zi[k] = q.z;
+        ax[k] = ay[k] = az[k] = 0.0;
+    }
+
+    auto consume = [&](const char* tile, int bytes) {
+        const double2* __restrict__ t = reinterpret_cast<const double2*>(tile);
+        const int n_j = bytes >> 5;
+#pragma unroll 4
+        for (int j = 0; j < n_j; ++j) {
+            const double2 a = t[2 * j];      // x y
+            const double2 b = t[2 * j + 1];  // z gm
+#pragma unroll
+            for (int k = 0; k < kP; ++k)
+                pair_f64<kZeroEps>(xi[k], yi[k], zi[k], a.x, a.y, b.x, b.y, eps2, ax[k], ay[k], az[k]);
+        }
+    };
+    stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 32, (j1 - j0) * 32, ring, bars, consume);
+
+    double* __restrict__ out = partial + (size_t)seg * 3 * n_i;
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+        const int li = li0 + k * kBlock;
+        if (li < n_i) {
+            out[li] = ax[k];
+            out[(size_t)n_i + li] = ay[k];
+            out[(size_t)2 * n_i + li] = az[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish: ordered segment reduction + (optionally) the leapfrog around it
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StreamIO;
+template <>
+struct StreamIO<double> {
+    static __device__ __forceinline__ double get(const double* s, int body, int c) { return s[(size_t)body * 4 + c]; }
+    static __device__ __forceinline__ void put(double* s, int body, int c, double v) { s[(size_t)body * 4 + c] = v; }
+};
+template <>
+struct StreamIO<float> {
+    static __device__ __forceinline__ float get(const float* s, int body, int c) {
+        return s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
+    }
+    static __device__ __forceinline__ void put(float* s, int body, int c, float v) {
+        s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)] = v;
+    }
+};
+
+// kStep == false: acc = sum of partials (K1).
+// kStep == true : closing kick, snapshot, and with NB_STEP_CONTINUE the next opening kick + drift (K2).
+template <typename T, bool kStep>
+__global__ void __launch_bounds__(256)
+finish_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, const T* __restrict__ stream_cur,
+              T* __restrict__ stream_next, T* __restrict__ vel, T* __restrict__ acc, T dt, T half_dt, int flags,
+              double* __restrict__ snap_pos, double* __restrict__ snap_vel, double* __restrict__ snap_acc) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_i) return;
+    T a[3] = {T(0), T(0), T(0)};
+    for (int s = 0; s < n_seg; ++s) {
+        const T* p = partial + (size_t)s * 3 * n_i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] += p[(size_t)c * n_i + li];
+    }
+    if (!kStep) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[(size_t)li * 3 + c] = a[c];
+        return;
+    }
+    const int gi = i0 + li;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T x = StreamIO<T>::get(stream_cur, gi, c);
+        T v = vel[(size_t)li * 3 + c];
+        v = mul_add_unfused(half_dt, a[c], v);  // closing kick, nbody.py:214
+        if (flags & NB_STEP_SNAPSHOT) {         // get_state(), nbody.py:250-259
+            if (snap_pos) snap_pos[(size_t)gi * 3 + c] = (double)x;
+            if (snap_vel) snap_vel[(size_t)gi * 3 + c] = (double)v;
+            if (snap_acc) snap_acc[(size_t)gi * 3 + c] = (double)a[c];
+        }
+        if (flags & NB_STEP_CONTINUE) {
+            v = mul_add_unfused(half_dt, a[c], v);  // next step's opening kick, nbody.py:205
+            x = mul_add_unfused(dt, v, x);          // drift, nbody.py:208
+            StreamIO<T>::put(stream_next, gi, c, x);
+        }
+        vel[(size_t)li * 3 + c] = v;
+        acc[(size_t)li * 3 + c] = a[c];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+kick_drift_kernel(const T* __restrict__ stream_cur, T* __restrict__ stream_next, T* __restrict__ vel,
+                  const T* __restrict__ acc, int i0, int n_i, T dt, T half_dt) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n_i) return;
+    const int gi = i0 + li;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T v = vel[(size_t)li * 3 + c];
+        v = mul_add_unfused(half_dt, acc[(size_t)li * 3 + c], v);           // nbody.py:205
+        const T x = mul_add_unfused(dt, v, StreamIO<T>::get(stream_cur, gi, c));  // nbody.py:208
+        StreamIO<T>::put(stream_next, gi, c, x);
+        vel[(size_t)li * 3 + c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_kernel(const double* __restrict__ pos, const void* __restrict__ masses, int masses_are_f32, int n, int n_pad,
+            T* __restrict__ stream) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    double x = 0.0, y = 0.0, z = 0.0, gm = 0.0;
+    if (i < n) {
+        x = pos[(size_t)i * 3 + 0];
+        y = pos[(size_t)i * 3 + 1];
+        z = pos[(size_t)i * 3 + 2];
+        const double m = masses_are_f32 ? (double)static_cast<const float*>(masses)[i]
+                                        : static_cast<const double*>(masses)[i];
+        gm = kG * m;  // G * masses[j], nbody.py:57
+    }
+    StreamIO<T>::put(stream, i, 0, (T)x);
+    StreamIO<T>::put(stream, i, 1, (T)y);
+    StreamIO<T>::put(stream, i, 2, (T)z);
+    StreamIO<T>::put(stream, i, 3, (T)gm);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_kernel(const T* __restrict__ stream, int n, double* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pos[(size_t)i * 3 + c] = (double)StreamIO<T>::get(stream, i, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch logic
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+    int n, n_pad, i0, n_i, seg_len, n_seg;
+};
+
+static int make_slab(int n, int i0, int n_i, Slab* out) {
+    NB_REQUIRE(n > 0, "n must be positive (got %d)", n);
+    NB_REQUIRE(i0 >= 0 && n_i > 0 && i0 + n_i <= n, "slab [%d, %d) outside system of %d bodies", i0, i0 + n_i, n);
+    out->n = n;
+    out->n_pad = nb_padded_bodies(n);
+    out->i0 = i0;
+    out->n_i = n_i;
+    nb_segment_plan(n, &out->seg_len, &out->n_seg);
+    return NB_OK;
+}
+
+// i-tile shapes.  Small slabs take the small tile so the grid still covers the SMs.
+template <typename T>
+struct Tile;
+template <>
+struct Tile<float> {
+    static constexpr int kPBig = 4, kBlockBig = 256, kPSmall = 2, kBlockSmall = 128;
+};
+template <>
+struct Tile<double> {
+    static constexpr int kPBig = 2, kBlockBig = 256, kPSmall = 1, kBlockSmall = 128;
+};
+
+template <int kP, int kBlock, bool kZeroEps>
+static void launch_force(const float* stream, const Slab& sl, float eps2, float* partial, cudaStream_t st) {
+    dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
+    force_f32_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
+                                                                     partial);
+}
+template <int kP, int kBlock, bool kZeroEps>
+static void launch_force(const double* stream, const Slab& sl, double eps2, double* partial, cudaStream_t st) {
+    dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
+    force_f64_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
+                                                                     partial);
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <typename T>
+static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st) {
+    const T eps2 = (T)(softening * softening);
+    const bool zero = !(eps2 > T(0));
+    using TL = Tile<T>;
+    // big tile only when it still yields at least ~4 CTAs per SM
+    const long ctas_big = (long)ceil_div(sl.n_i, TL::kPBig * TL::kBlockBig) * sl.n_seg;
+    const bool big = ctas_big >= 4L * sm_count();
+    if (big) {
+        if (zero) launch_force<TL::kPBig, TL::kBlockBig, true>(stream, sl, eps2, partial, st);
+        else launch_force<TL::kPBig, TL::kBlockBig, false>(stream, sl, eps2, partial, st);
+    } else {
+        if (zero) launch_force<TL::kPSmall, TL::kBlockSmall, true>(stream, sl, eps2, partial, st);
+        else launch_force<TL::kPSmall, TL::kBlockSmall, false>(stream, sl, eps2, partial, st);
+    }
+    return check_launch("force kernel");
+}
+
+template <typename T>
+static int accel_impl(const T* stream, int n, int i0, int n_i, double softening, T* acc, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+    Slab sl;
+    if (int rc = make_slab(n, i0, n_i, &sl)) return rc;
+    NB_REQUIRE(stream && acc && ws, "null pointer argument");
+    NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
+               nb_workspace_bytes(n, n_i, sizeof(T) == 8));
+    T* partial = static_cast<T*>(ws);
+    if (int rc = force_pass<T>(stream, sl, softening, partial, st)) return rc;
+    finish_kernel<T, false><<<ceil_div(n_i, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, nullptr, nullptr, nullptr,
+                                                                 acc, T(0), T(0), 0, nullptr, nullptr, nullptr);
+    return check_launch("finish kernel");
+}
+
+template <typename T>
+static int step_impl(const T* cur, T* next, T* vel, T* acc, int n, int i0, int n_i, double dt, double softening,
+                     int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Slab sl;
+    if (int rc = make_slab(n, i0, n_i, &sl)) return rc;
+    NB_REQUIRE(cur && vel && acc && ws, "null pointer argument");
+    NB_REQUIRE(!(flags & NB_STEP_CONTINUE) || next, "NB_STEP_CONTINUE needs stream_next");
+    NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
+               nb_workspace_bytes(n, n_i, sizeof(T) == 8));
+    T* partial = static_cast<T*>(ws);
+    if (int rc = force_pass<T>(cur, sl, softening, partial, st)) return rc;
+    const double half_dt = 0.5 * dt;  // "0.5 * self.dt" is evaluated first, nbody.py:205
+    finish_kernel<T, true><<<ceil_div(n_i, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, next, vel, acc, (T)dt,
+                                                                (T)half_dt, flags, sp, sv, sa);
+    return check_launch("finish kernel");
+}
+
+template <typename T>
+static int kick_drift_impl(const T* cur, T* next, T* vel, const T* acc, int n, int i0, int n_i, double dt,
+                           cudaStream_t st) {
+    Slab sl;
+    if (int rc = make_slab(n, i0, n_i, &sl)) return rc;
+    NB_REQUIRE(cur && next && vel && acc, "null pointer argument");
+    const double half_dt = 0.5 * dt;
+    kick_drift_kernel<T><<<ceil_div(n_i, 256), 256, 0, st>>>(cur, next, vel, acc, i0, n_i, (T)dt, (T)half_dt);
+    return check_launch("kick_drift kernel");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+snapshot0_kernel(const T* __restrict__ stream, const T* __restrict__ vel, const T* __restrict__ acc, int n,
+                 double* __restrict__ sp, double* __restrict__ sv, double* __restrict__ sa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (sp) sp[(size_t)i * 3 + c] = (double)StreamIO<T>::get(stream, i, c);
+        if (sv) sv[(size_t)i * 3 + c] = (double)vel[(size_t)i * 3 + c];
+        if (sa) sa[(size_t)i * 3 + c] = (double)acc[(size_t)i * 3 + c];
+    }
+}
+
+template <typename T>
+static int run_impl(T* sa_, T* sb_, T* vel, T* acc, int n, double dt, double softening, int n_steps, int save_interval,
+                    double* sp, double* sv, double* sa, void* ws, size_t ws_bytes, int* final_in_a, cudaStream_t st) {
+    NB_REQUIRE(n_steps >= 0 && save_interval >= 1, "n_steps >= 0 and save_interval >= 1 required");
+    NB_REQUIRE(sa_ && sb_ && vel && acc, "null pointer argument");
+    const size_t row = (size_t)n * 3;
+    if (sp || sv || sa) {  // states.append(get_state()) before the loop, nbody.py:235
+        snapshot0_kernel<T><<<ceil_div(n, 256), 256, 0, st>>>(sa_, vel, acc, n, sp, sv, sa);
+        if (int rc = check_launch("snapshot0 kernel")) return rc;
+    }
+    T* cur = sa_;
+    T* next = sb_;
+    if (n_steps > 0) {
+        if (int rc = kick_drift_impl<T>(cur, next, vel, acc, n, 0, n, dt, st)) return rc;
+        T* t = cur; cur = next; next = t;
+    }
+    size_t snap = 1;
+    for (int k = 1; k <= n_steps; ++k) {
+        int flags = 0;
+        if (k < n_steps) flags |= NB_STEP_CONTINUE;
+        const bool save = (k % save_interval) == 0;  // nbody.py:240
+        if (save) flags |= NB_STEP_SNAPSHOT;
+        if (int rc = step_impl<T>(cur, next, vel, acc, n, 0, n, dt, softening, flags,
+                                  (save && sp) ? sp + snap * row : nullptr, (save && sv) ? sv + snap * row : nullptr,
+                                  (save && sa) ? sa + snap * row : nullptr, ws, ws_bytes, st))
+            return rc;
+        if (save) ++snap;
+        if (k < n_steps) { T* t = cur; cur = next; next = t; }
+    }
+    if (final_in_a) *final_in_a = (cur == sa_) ? 1 : 0;
+    return NB_OK;
+}
+
+}  // namespace nb
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nb_pack_f64(const double* pos, const void* masses, int masses_are_f32, int n, double* stream, nb_stream_t s) {
+    NB_REQUIRE(pos && masses && stream && n > 0, "nb_pack_f64: bad argument");
+    const int n_pad = nb_padded_bodies(n);
+    nb::pack_kernel<double><<<nb::ceil_div(n_pad, 256), 256, 0, (cudaStream_t)s>>>(pos, masses, masses_are_f32, n,
+                                                                                    n_pad, stream);
+    return nb::check_launch("pack kernel");
+}
+int nb_pack_f32(const double* pos, const void* masses, int masses_are_f32, int n, float* stream, nb_stream_t s) {
+    NB_REQUIRE(pos && masses && stream && n > 0, "nb_pack_f32: bad argument");
+    const int n_pad = nb_padded_bodies(n);
+    nb::pack_kernel<float><<<nb::ceil_div(n_pad, 256), 256, 0, (cudaStream_t)s>>>(pos, masses, masses_are_f32, n,
+                                                                                   n_pad, stream);
+    return nb::check_launch("pack kernel");
+}
+int nb_unpack_f64(const double* stream, int n, double* pos, nb_stream_t s) {
+    NB_REQUIRE(pos && stream && n > 0, "nb_unpack_f64: bad argument");
+    nb::unpack_kernel<double><<<nb::ceil_div(n, 256), 256, 0, (cudaStream_t)s>>>(stream, n, pos);
+    return nb::check_launch("unpack kernel");
+}
+int nb_unpack_f32(const float* stream, int n, double* pos, nb_stream_t s) {
+    NB_REQUIRE(pos && stream && n > 0, "nb_unpack_f32: bad argument");
+    nb::unpack_kernel<float><<<nb::ceil_div(n, 256), 256, 0, (cudaStream_t)s>>>(stream, n, pos);
+    return nb::check_launch("unpack kernel");
+}
+
+int nb_accel_f64(const double* stream, int n, int i0, int n_i, double softening, double* acc, void* ws,
+                 size_t ws_bytes, nb_stream_t s) {
+    return nb::accel_impl<double>(stream, n, i0, n_i, softening, acc, ws, ws_bytes, (cudaStream_t)s);
+}
+int nb_accel_f32(const float* stream, int n, int i0, int n_i, double softening, float* acc, void* ws, size_t ws_bytes,
+                 nb_stream_t s) {
+    return nb::accel_impl<float>(stream, n, i0, n_i, softening, acc, ws, ws_bytes, (cudaStream_t)s);
+}
+
+int nb_kick_drift_f64(const double* cur, double* next, double* vel, const double* acc, int n, int i0, int n_i,
+                      double dt, nb_stream_t s) {
+    return nb::kick_drift_impl<double>(cur, next, vel, acc, n, i0, n_i, dt, (cudaStream_t)s);
+}
+int nb_kick_drift_f32(const float* cur, float* next, float* vel, const float* acc, int n, int i0, int n_i, double dt,
+                      nb_stream_t s) {
+    return nb::kick_drift_impl<float>(cur, next, vel, acc, n, i0, n_i, dt, (cudaStream_t)s);
+}
+
+int nb_step_f64(const double* cur, double* next, double* vel, double* acc, int n, int i0, int n_i, double dt,
+                double softening, int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+                nb_stream_t s) {
+    return nb::step_impl<double>(cur, next, vel, acc, n, i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes,
+                                 (cudaStream_t)s);
+}
+int nb_step_f32(const float* cur, float* next, float* vel, float* acc, int n, int i0, int n_i, double dt,
+                double softening, int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+                nb_stream_t s) {
+    return nb::step_impl<float>(cur, next, vel, acc, n, i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes,
+                                (cudaStream_t)s);
+}
+
+int nb_run_f64(double* stream_a, double* stream_b, double* vel, double* acc, int n, double dt, double softening,
+               int n_steps, int save_interval, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+               int* final_in_a, nb_stream_t s) {
+    return nb::run_impl<double>(stream_a, stream_b, vel, acc, n, dt, softening, n_steps, save_interval, sp, sv, sa, ws,
+                                ws_bytes, final_in_a, (cudaStream_t)s);
+}
+int nb_run_f32(float* stream_a, float* stream_b, float* vel, float* acc, int n, double dt, double softening,
+               int n_steps, int save_interval, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+               int* final_in_a, nb_stream_t s) {
+    return nb::run_impl<float>(stream_a, stream_b, vel, acc, n, dt, softening, n_steps, save_interval, sp, sv, sa, ws,
+                               ws_bytes, final_in_a, (cudaStream_t)s);
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+"""ctypes binding of libnbody_b200.so plus the torch plumbing around it (device memory, streams).
+
+This is the only module that touches the CUDA library.  There is no CPU path: if the library is
+missing, or no CUDA device is visible, every entry point raises ``EngineUnavailable``.
+
+PyTorch's role here is plumbing only -- allocating device/pinned tensors, host<->device copies and
+the current stream.  All arithmetic of the hot path runs in the hand-written sm_100a kernels
+behind the C ABI declared in ``include/nbody_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent.parent
+LIB_PATH = _PKG / "lib" / "libnbody_b200.so"
+
+NB_STEP_CONTINUE = 1
+NB_STEP_SNAPSHOT = 2
+
+# N at or below which a single system runs through the one-launch ensemble kernel (K3, B = 1)
+# instead of one force launch per step (K1/K2).
+SMALL_SYSTEM_MAX_BODIES = 512
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA engine cannot run here (library not built, or no GPU).  There is no fallback."""
+
+
+_vp, _ci, _cd, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+_ip = ctypes.POINTER(ctypes.c_int)
+
+_SIGNATURES = {
+    "nb_abi_version": (_ci, []),
+    "nb_last_error": (ctypes.c_char_p, []),
+    "nb_device_info": (_ci, [_ci, _ip, _ip, _ip, _ip]),
+    "nb_probe_fma_peak": (_ci, [_ci, ctypes.POINTER(ctypes.c_double), _vp, _vp]),
+    "nb_padded_bodies": (_ci, [_ci]),
+    "nb_segment_plan": (_ci, [_ci, _ip, _ip]),
+    "nb_workspace_bytes": (_sz, [_ci, _ci, _ci]),
+    "nb_pack_f64": (_ci, [_vp, _vp, _ci, _ci, _vp, _vp]),
+    "nb_pack_f32": (_ci, [_vp, _vp, _ci, _ci, _vp, _vp]),
+    "nb_unpack_f64": (_ci, [_vp, _ci, _vp, _vp]),
+    "nb_unpack_f32": (_ci, [_vp, _ci, _vp, _vp]),
+    "nb_accel_f64": (_ci, [_vp, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
+    "nb_accel_f32": (_ci, [_vp, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
+    "nb_kick_drift_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _vp]),
+    "nb_kick_drift_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _vp]),
+    "nb_step_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nb_step_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nb_run_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
+    "nb_run_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
+    "nb_ensemble_max_bodies": (_ci, []),
+    "nb_ensemble_workspace_bytes": (_sz, [_ci]),
+    "nb_ensemble_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
+                              _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
+    "nb_ensemble_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
+                              _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
+    "nb_energy_workspace_bytes": (_sz, [_ci, _ci]),
+    "nb_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
+    "nbh_accel_direct": (_ci, [_vp, _vp, _ci, _ci, _cd, _ci, _vp]),
+    "nbh_run": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _vp, _vp, _vp]),
+    "nbh_ensemble_run": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _vp, _vp, _vp]),
+    "nbh_total_energy": (_ci, [_vp, _vp, _vp, _ci, _ci, _cd, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the C-ABI library and declare every signature.  Works without a GPU."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = Path(os.environ.get("NBODY_B200_LIB", LIB_PATH))
+        if not path.exists():
+            raise EngineUnavailable(
+                f"{path} not found: build it with `python nbody-gnn-hpc_b200/build.py` "
+                "(nvcc, sm_100a).  This engine has no CPU fallback.")
+        lib = ctypes.CDLL(str(path))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.nb_abi_version() != 1:
+            raise EngineUnavailable(f"{path}: unexpected ABI version {lib.nb_abi_version()}")
+        _lib = lib
+        return lib
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """One CUDA device's view of the library.  Mirrors the reference operations one to one."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise EngineUnavailable("no CUDA device visible: the B200 engine has no CPU fallback")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        sm, maj, minr, clk = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.nb_device_info(self.device.index or 0, sm, maj, minr, clk))
+        self.sm_count, self.cc, self.sm_clock_khz = sm.value, (maj.value, minr.value), clk.value
+        if maj.value != 10:
+            raise EngineUnavailable(
+                f"device compute capability {maj.value}.{minr.value}: this library holds sm_100a code only")
+        self.launches = 0  # kernels of this library enqueued through this object (for bench.py)
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(f"libnbody_b200: {self.lib.nb_last_error().decode()} (code {rc})")
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def _suffix(self, dtype) -> str:
+        d = np.dtype(dtype)
+        if d == np.float64:
+            return "f64"
+        if d == np.float32:
+            return "f32"
+        raise ValueError(f"engine dtype must be float64 or float32, got {d}")
+
+    def _tdtype(self, dtype):
+        torch = _torch()
+        return torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+
+    def to_device(self, arr, dtype=None, pinned: bool = True):
+        """Host ndarray -> device tensor through pinned staging (dtype conversion on device)."""
+        torch = _torch()
+        a = np.ascontiguousarray(arr)
+        src = torch.from_numpy(a)
+        if pinned and a.nbytes >= (1 << 16):
+            stage = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            stage.copy_(src)
+            dev = stage.to(self.device, non_blocking=True)
+        else:
+            dev = src.to(self.device)
+        if dtype is not None and dev.dtype != dtype:
+            dev = dev.to(dtype)
+        return dev
+
+    def to_host(self, t, pinned: bool = True) -> np.ndarray:
+        """Device tensor -> fresh host float64 ndarray (pinned block from torch's host cache)."""
+        torch = _torch()
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if pinned and t.numel() * 8 >= (1 << 16):
+            host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return host.numpy()
+        return t.cpu().numpy()
+
+    def _masses_dev(self, masses):
+        m = np.asarray(masses)
+        if m.dtype == np.float32:
+            return self.to_device(m, pinned=False), 1
+        return self.to_device(np.asarray(m, dtype=np.float64), pinned=False), 0
+
+    def fma_peak_tflops(self, mode: str) -> float:
+        """Measured FMA-pipe peak: mode 'ffma', 'ffma2' or 'dfma' (TFLOP/s, 2 flops per FMA)."""
+        torch = _torch()
+        out = ctypes.c_double()
+        scratch = torch.zeros(1, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.nb_probe_fma_peak({"ffma": 0, "ffma2": 1, "dfma": 2}[mode], out,
+                                                   self._p(scratch), self._stream()))
+        return out.value
+
+    def padded_bodies(self, n: int) -> int:
+        return int(self.lib.nb_padded_bodies(int(n)))
+
+    def segment_plan(self, n: int):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self.lib.nb_segment_plan(int(n), a, b)
+        return a.value, b.value
+
+    def workspace(self, n: int, n_i: int, dtype):
+        torch = _torch()
+        nbytes = int(self.lib.nb_workspace_bytes(int(n), int(n_i), int(np.dtype(dtype) == np.float64)))
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes
+
+    # ---- device-level operations (tensors in, tensors out; used by nbody.py and sharded.py) ----
+    def pack(self, pos_dev, masses_dev, masses_f32: int, n: int, dtype):
+        """API-layout positions (n,3) float64 + masses -> stream-layout tensor of `dtype`."""
+        torch = _torch()
+        sfx = self._suffix(dtype)
+        stream = torch.empty(self.padded_bodies(n) * 4, dtype=self._tdtype(dtype), device=self.device)
+        self._check(getattr(self.lib, f"nb_pack_{sfx}")(self._p(pos_dev), self._p(masses_dev), masses_f32, n,
+                                                         self._p(stream), self._stream()))
+        self.launches += 1
+        return stream
+
+    def unpack(self, stream, n: int):
+        torch = _torch()
+        sfx = "f64" if stream.dtype == torch.float64 else "f32"
+        pos = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        self._check(getattr(self.lib, f"nb_unpack_{sfx}")(self._p(stream), n, self._p(pos), self._stream()))
+        self.launches += 1
+        return pos
+
+    def accel_slab(self, stream, n: int, i0: int, n_i: int, softening: float, ws=None):
+        """K1 on rows [i0, i0+n_i): returns (n_i,3) tensor in the stream's dtype."""
+        torch = _torch()
+        dtype = np.float64 if stream.dtype == torch.float64 else np.float32
+        sfx = self._suffix(dtype)
+        if ws is None:
+            ws = self.workspace(n, n_i, dtype)
+        acc = torch.empty((n_i, 3), dtype=stream.dtype, device=self.device)
+        self._check(getattr(self.lib, f"nb_accel_{sfx}")(self._p(stream), n, i0, n_i, float(softening), self._p(acc),
+                                                          self._p(ws[0]), ws[1], self._stream()))
+        self.launches += 2
+        return acc
+
+    def kick_drift_slab(self, cur, nxt, vel, acc, n: int, i0: int, n_i: int, dt: float):
+        torch = _torch()
+        sfx = "f64" if cur.dtype == torch.float64 else "f32"
+        self._check(getattr(self.lib, f"nb_kick_drift_{sfx}")(self._p(cur), self._p(nxt), self._p(vel), self._p(acc),
+                                                               n, i0, n_i, float(dt), self._stream()))
+        self.launches += 1
+
+    def step_slab(self, cur, nxt, vel, acc, n: int, i0: int, n_i: int, dt: float, softening: float, flags: int,
+                  snap_pos, snap_vel, snap_acc, ws):
+        torch = _torch()
+        sfx = "f64" if cur.dtype == torch.float64 else "f32"
+        self._check(getattr(self.lib, f"nb_step_{sfx}")(
+            self._p(cur), self._p(nxt), self._p(vel), self._p(acc), n, i0, n_i, float(dt), float(softening),
+            int(flags), self._p(snap_pos), self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1],
+            self._stream()))
+        self.launches += 2
+
+    # ---- host-level operations (ndarrays in, ndarrays out; the reference's call shapes) ----------
+    def accelerations(self, positions, masses, softening: float, dtype=np.float64) -> np.ndarray:
+        """compute_accelerations_direct (reference nbody.py:22-66) -> new (N,3) float64 ndarray."""
+        torch = _torch()
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        n = pos.shape[0]
+        with torch.cuda.device(self.device):
+            pos_d = self.to_device(pos)
+            m_d, f32 = self._masses_dev(masses)
+            stream = self.pack(pos_d, m_d, f32, n, dtype)
+            acc = self.accel_slab(stream, n, 0, n, softening)
+            return self.to_host(acc)
+
+    def run(self, positions, velocities, accelerations, masses, dt: float, softening: float, n_steps: int,
+            save_interval: int = 1, dtype=np.float64, snapshots: bool = True) -> dict:
+        """The loop of NBodySimulator.run (reference nbody.py:232-248) from an explicit (x, v, a).
+
+        Returns snapshot stacks (n_snap, N, 3) float64 -- row 0 is the entry state -- and the final
+        synchronised state.
+        """
+        torch = _torch()
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        n = pos.shape[0]
+        if n <= SMALL_SYSTEM_MAX_BODIES:
+            out = self.ensemble(pos[None], np.asarray(velocities, dtype=np.float64)[None], masses, dt, softening,
+                                n_steps, save_interval, dtype=dtype, a0=np.asarray(accelerations, dtype=np.float64)[None],
+                                snapshots=snapshots)
+            res = {"final_positions": out["final_positions"][0], "final_velocities": out["final_velocities"][0],
+                   "final_accelerations": out["final_accelerations"][0]}
+            if snapshots:
+                res.update(positions=out["positions"][0], velocities=out["velocities"][0],
+                           accelerations=out["accelerations"][0])
+            return res
+        sfx = self._suffix(dtype)
+        td = self._tdtype(dtype)
+        n_snap = 1 + n_steps // save_interval
+        with torch.cuda.device(self.device):
+            pos_d = self.to_device(pos)
+            m_d, f32 = self._masses_dev(masses)
+            sa = self.pack(pos_d, m_d, f32, n, dtype)
+            sb = sa.clone()
+            vel = self.to_device(np.asarray(velocities, dtype=np.float64), td)
+            acc = self.to_device(np.asarray(accelerations, dtype=np.float64), td)
+            ws = self.workspace(n, n, dtype)
+            if snapshots:
+                sp = torch.empty((n_snap, n, 3), dtype=torch.float64, device=self.device)
+                sv = torch.empty_like(sp)
+                sc = torch.empty_like(sp)
+            else:
+                sp = sv = sc = None
+            fin = ctypes.c_int(1)
+            self._check(getattr(self.lib, f"nb_run_{sfx}")(
+                self._p(sa), self._p(sb), self._p(vel), self._p(acc), n, float(dt), float(softening), int(n_steps),
+                int(save_interval), self._p(sp), self._p(sv), self._p(sc), self._p(ws[0]), ws[1], fin,
+                self._stream()))
+            self.launches += (1 if snapshots else 0) + (1 if n_steps else 0) + 2 * n_steps
+            final_pos = self.unpack(sa if fin.value else sb, n)
+            res = {"final_positions": self.to_host(final_pos), "final_velocities": self.to_host(vel),
+                   "final_accelerations": self.to_host(acc)}
+            if snapshots:
+                res.update(positions=self.to_host(sp), velocities=self.to_host(sv), accelerations=self.to_host(sc))
+            return res
+
+    def ensemble_device(self, x, v, a, m_d, masses_f32: int, mass_stride: int, B: int, N: int, dt: float,
+                        softening: float, n_steps: int, save_interval: int, dtype, compute_a0: bool,
+                        write_initial: bool, out_x, out_v, out_a, n_snap_total: int, snap_offset: int, ws=None):
+        """K3 on device tensors (state in/out, snapshot stacks out).  One launch."""
+        torch = _torch()
+        sfx = self._suffix(dtype)
+        if ws is None:
+            nbytes = int(self.lib.nb_ensemble_workspace_bytes(B))
+            ws = (torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes)
+        self._check(getattr(self.lib, f"nb_ensemble_{sfx}")(
+            self._p(x), self._p(v), self._p(a), self._p(m_d), masses_f32, mass_stride, B, N, float(dt),
+            float(softening), int(n_steps), int(save_interval), int(bool(compute_a0)), int(bool(write_initial)),
+            self._p(out_x), self._p(out_v), self._p(out_a), int(n_snap_total), int(snap_offset),
+            self._p(ws[0]), ws[1], self._stream()))
+        self.launches += 1
+
+    def ensemble(self, x0, v0, masses, dt: float, softening: float, n_steps: int, save_interval: int = 1,
+                 dtype=np.float64, a0=None, snapshots: bool = True) -> dict:
+        """B independent systems (reference generate_data.py:32-58,142-149): host arrays in and out.
+
+        x0, v0: (B,N,3); masses: (N,) shared or (B,N).  a0 None -> evaluated from x0 (what the
+        scripts do after assigning the shared masses, generate_data.py:47).
+        """
+        torch = _torch()
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        B, N = x0.shape[0], x0.shape[1]
+        m = np.asarray(masses)
+        if m.ndim == 1:
+            mass_stride = 0
+        elif m.shape == (B, N):
+            mass_stride = N
+        else:
+            raise ValueError(f"masses must be (N,) or (B,N); got {m.shape}")
+        if N > int(self.lib.nb_ensemble_max_bodies()):
+            raise ValueError(f"ensemble kernel holds at most {self.lib.nb_ensemble_max_bodies()} bodies per system")
+        n_snap = 1 + n_steps // save_interval
+        with torch.cuda.device(self.device):
+            x = self.to_device(x0)
+            v = self.to_device(v0)
+            if a0 is None:
+                a = torch.zeros_like(x)
+            else:
+                a = self.to_device(np.ascontiguousarray(a0, dtype=np.float64))
+            m_d, f32 = self._masses_dev(np.ascontiguousarray(m))
+            if snapshots:
+                ox = torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=self.device)
+                ov = torch.empty_like(ox)
+                oa = torch.empty_like(ox)
+            else:
+                ox = ov = oa = None
+            self.ensemble_device(x, v, a, m_d, f32, mass_stride, B, N, dt, softening, n_steps, save_interval, dtype,
+                                 compute_a0=a0 is None, write_initial=True, out_x=ox, out_v=ov, out_a=oa,
+                                 n_snap_total=n_snap, snap_offset=0)
+            res = {"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
+                   "final_accelerations": self.to_host(a)}
+            if snapshots:
+                res.update(positions=self.to_host(ox), velocities=self.to_host(ov), accelerations=self.to_host(oa))
+            return res
+
+    def energy(self, positions, velocities, masses, softening: float):
+        """compute_total_energy (reference nbody.py:101-130) -> (K, U, K+U) Python floats."""
+        torch = _torch()
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        n = pos.shape[0]
+        with torch.cuda.device(self.device):
+            pos_d = self.to_device(pos)
+            vel_d = self.to_device(np.ascontiguousarray(velocities, dtype=np.float64))
+            m_d, f32 = self._masses_dev(masses)
+            ku = self.energy_slab(pos_d, vel_d, m_d, f32, n, 0, n, softening)
+            k, u = (float(t) for t in ku.cpu())
+        return k, u, k + u
+
+    def energy_slab(self, pos_d, vel_d, m_d, masses_f32: int, n: int, i0: int, n_i: int, softening: float):
+        torch = _torch()
+        nbytes = int(self.lib.nb_energy_workspace_bytes(n, n_i))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ku = torch.empty(2, dtype=torch.float64, device=self.device)
+        self._check(self.lib.nb_energy_f64(self._p(pos_d), self._p(vel_d), self._p(m_d), masses_f32, n, i0, n_i,
+                                           float(softening), self._p(ku), self._p(ws), nbytes, self._stream()))
+        self.launches += 2
+        return ku
+
+
+_engines: dict = {}
+
+
+def get_engine(device=None) -> Engine:
+    """The process-wide Engine for `device` (default: torch's current CUDA device).  CUDA is
+    initialised on first use, never at import time, so fork-based worker pools keep working."""
+    torch = _torch()
+    if device is None:
+        if not torch.cuda.is_available():
+            load_library()  # report a missing library first: it is the more actionable error
+            raise EngineUnavailable("no CUDA device visible: the B200 engine has no CPU fallback")
+        key = (os.getpid(), torch.cuda.current_device())
+    else:
+        key = (os.getpid(), torch.device(device).index or 0)
+    eng = _engines.get(key)
+    if eng is None:
+        eng = Engine(torch.device("cuda", key[1]))
+        _engines[key] = eng
+    return eng
