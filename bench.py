@@ -1,0 +1,477 @@
+#!/usr/bin/env python3
+"""Benchmark of the direct-sum gravity + leapfrog hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+Workloads (BASELINE.json `configs`):
+  ensemble (default, configs[1]): the data-generation ensemble, 300 independent simulations x 200
+      bodies x 400 steps, float64, snapshots every step.  One bench "step" = one whole ensemble.
+      N GPUs: every rank runs its own 300 simulations (weak scaling, no communication).
+  single:  one system of --bodies bodies, float32 or float64, --sim-steps leapfrog steps per bench step.
+  sharded: the same single system split by i-slab over the ranks with one position all-gather per
+      leapfrog step (strong scaling).
+
+One JSON line is printed by rank 0.  `value` is the whole-job metric with inputs resident in HBM;
+`e2e` is the same metric through the public host-array API (host->device and device->host copies
+inside the timed region).  `roofline`, `cpu_baseline`, `clocks` as described in DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "nbody-gnn-hpc_b200"
+for _p in (str(ROOT), str(PKG)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "pairwise interactions/s (1e9)"
+UNIT = "Ginteractions/s"
+FLOPS_PER_INTERACTION = 20.0      # BASELINE.json north_star convention
+ENS_B, ENS_N, ENS_STEPS = 300, 200, 400
+
+
+def measured_peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text())
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "_fallback": True}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display_clocks"}
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML missing: report that, do not fail the benchmark
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self) -> dict:
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places this file touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_ensemble_sample(n_sims: int, seed0: int = 42):
+    """Time the oracle port on n_sims data-generation simulations (one host thread per simulation,
+    all cores busy -- the reference's mp.Pool of single-threaded workers).  Returns (Gint/s, seconds, cores)."""
+    import oracle
+    from hpc import ics
+    oracle.build()
+    cores = oracle.num_threads()
+    x0, v0, m32 = ics.datagen_ensemble_ic(n_sims, ENS_N, seed=seed0)
+    t0 = time.perf_counter()
+    oracle.ensemble_run(x0, v0, m32, 1e-3, 1e-9, ENS_STEPS, 1, outputs=True)
+    dt = time.perf_counter() - t0
+    inter = n_sims * ENS_STEPS * ENS_N * (ENS_N - 1.0)
+    return inter / dt / 1e9, dt, cores
+
+
+def cpu_single_sample(n: int, seed: int = 7):
+    """One force evaluation of the oracle port with all host threads (large-N CPU figure)."""
+    import oracle
+    from hpc import ics
+    oracle.build()
+    x, _, m = ics.plummer_ic(n, seed=seed)
+    oracle.accel_direct(x[:256], m[:256], 0.01)
+    t0 = time.perf_counter()
+    oracle.accel_direct(x, m, 0.01)
+    dt = time.perf_counter() - t0
+    return n * (n - 1.0) / dt / 1e9, dt, oracle.num_threads()
+
+
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is Numba-JIT Python
+    and /root/reference does not exist on the GPU box) on the host cores, same metric and config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = oracle.num_threads()
+    if args.workload == "ensemble":
+        n_sims = max(2 * cores, 8)
+        sample = f"{n_sims} of {ENS_B} simulations x {ENS_N} bodies x {ENS_STEPS} steps per step, {cores} threads"
+        fn = lambda: cpu_ensemble_sample(n_sims)      # noqa: E731
+        cfg = {"workload": f"datagen ensemble {ENS_B}x{ENS_N}x{ENS_STEPS} fp64 (configs[1])"}
+    else:
+        n = min(args.bodies, 16384)
+        sample = f"1 force evaluation at N={n} per step (flat in N), {cores} threads"
+        fn = lambda: cpu_single_sample(n)              # noqa: E731
+        cfg = {"workload": f"single system N={args.bodies} (CPU timed at N={n})"}
+    for _ in range(args.warmup):
+        fn()
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, s, _ = fn()
+        vals.append(v)
+        secs.append(s)
+    value = float(np.sum([v * s for v, s in zip(vals, secs)]) / np.sum(secs))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * float(np.mean(secs)), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "isa": oracle.isa_level()},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus: int):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier_sync(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world: int) -> float:
+    import torch
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_steps(fn, steps: int, warmup: int, world: int):
+    """W untimed + K timed calls of fn, bracketed by barrier + synchronize; device time (CUDA events on
+    the launching stream), max over ranks.  Returns (seconds, per-step kernel-region ms list)."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier_sync(world)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
+
+
+def bench_ensemble(args, world, rank, local):
+    import torch
+    from hpc import _cuda, ics
+    from hpc.ensemble import simulate_ensemble
+    eng = _cuda.get_engine(local)
+    B, N, T = ENS_B, ENS_N, ENS_STEPS
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, N, seed=42, first_sim=rank * B)
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    dev = eng.device
+    x0_d, v0_d = eng.to_device(x0), eng.to_device(v0)
+    x, v, a = x0_d.clone(), v0_d.clone(), torch.zeros_like(x0_d)
+    m_d, f32 = eng._masses_dev(m32)
+    n_snap = T + 1
+    # two output sets, alternated: every step writes 1.73 GB of fresh lines (>> 126 MB L2)
+    outs = [tuple(torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=dev) for _ in range(3)) for _ in range(2)]
+    nbytes = int(eng.lib.nb_ensemble_workspace_bytes(B))
+    ws = (torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes)
+    kernel_ms = []
+    state = {"i": 0}
+
+    def step():
+        ox, ov, oa = outs[state["i"] & 1]
+        state["i"] += 1
+        x.copy_(x0_d)
+        v.copy_(v0_d)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        eng.ensemble_device(x, v, a, m_d, f32, 0, B, N, 1e-3, 1e-9, T, 1, dtype, True, True, ox, ov, oa, n_snap, 0, ws)
+        k1.record()
+        kernel_ms.append((k0, k1))
+
+    launches0 = eng.launches
+    with ClockSampler(local) as clk:
+        secs = time_steps(step, args.steps, args.warmup, world)
+    launches = (eng.launches - launches0) * args.steps // (args.steps + args.warmup)
+    k_ms = [a_.elapsed_time(b_) for a_, b_ in kernel_ms[args.warmup:]]
+    inter_step = B * T * N * (N - 1.0)                      # per rank per bench step (a_0 evaluation not counted)
+    value = world * args.steps * inter_step / secs / 1e9
+
+    # e2e through the public API: host arrays in, host arrays out
+    def e2e_step():
+        out = simulate_ensemble(x0, v0, m32, dt=1e-3, softening=1e-9, n_steps=T, save_interval=1, dtype=dtype, device=local)
+        return out["positions"][0, -1, 0, 0]
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier_sync(world)
+    e2e_secs = max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = world * e2e_steps * inter_step / e2e_secs / 1e9
+    h2d = x0.nbytes + v0.nbytes + m32.nbytes
+    d2h = 3 * B * n_snap * N * 3 * 8 + 3 * B * N * 3 * 8
+
+    peaks = measured_peaks()
+    k_mean = float(np.mean(k_ms)) * 1e-3
+    pipe = "fp64" if dtype == np.float64 else "fp32"
+    lanes = 64 if dtype == np.float64 else 128
+    peak_tf = eng.sm_count * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    achieved_tf = inter_step * FLOPS_PER_INTERACTION / k_mean / 1e12
+    snap_bytes = B * n_snap * N * 72.0
+    prof = profile_summary().get("ensemble_kernel", {})
+    roofline = {
+        "kernel": f"ensemble_kernel<{'double' if dtype == np.float64 else 'float'}>", "bound": pipe,
+        "achieved": round(achieved_tf, 3), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
+        "frac": round(achieved_tf / peak_tf, 4),
+        "peak_source": f"{eng.sm_count} SMs x {lanes} lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
+                       f"{FLOPS_PER_INTERACTION:.0f} flop/interaction convention",
+        "peak_probe": round(eng.fma_peak_tflops("dfma" if dtype == np.float64 else "ffma"), 2),
+        "kernel_ms": round(k_mean * 1e3, 4),
+        "traffic": prof.get("dram_bytes_per_launch"),
+        "hbm": {"algorithmic_bytes": snap_bytes, "achieved": round(snap_bytes / k_mean / 1e9, 1),
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(snap_bytes / k_mean / 1e9 / peaks["hbm_gbs"], 4),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" + (" (fallback)" if peaks.get("_fallback") else " (measured)")},
+    }
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_sims = 8 * (os.cpu_count() or 8)
+        v_cpu, s_cpu, cores = cpu_ensemble_sample(n_sims)
+        cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_sims} of {B} simulations x {N} bodies x {T} steps, one thread per simulation, {s_cpu:.1f} s"}
+    extra = single_system_extras(eng) if (rank == 0 and not args.no_extras) else None
+    return {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"datagen ensemble {B}x{N}x{T} per GPU, fp64 snapshots every step (configs[1])",
+                   "simulations_per_gpu": B, "bodies": N, "sim_steps": T, "save_interval": 1,
+                   "ics": "reference-default (seeded uniform box, shared float32 masses)",
+                   "l2": "each step writes 1.73 GB of fresh snapshot lines (>> 126 MB L2); two output sets alternate",
+                   "parallelism": f"ensemble split over {world} rank(s), no communication"},
+        "sim_steps_per_s": round(world * args.steps * B * T / secs, 1),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(1e3 * e2e_secs / e2e_steps, 3), "steps": e2e_steps,
+                "api": "hpc.ensemble.simulate_ensemble(host ndarrays) -> host ndarrays"},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
+        "also": extra,
+    }
+
+
+def single_system_extras(eng) -> dict:
+    """Single-system force kernels at N = 65,536 (north_star's >= 70% FP32 target is quoted on N >= 65k)."""
+    import torch
+    from hpc import ics
+    out = {}
+    n = 65536
+    x, _, m = ics.plummer_ic(n, seed=7)
+    pos_d = eng.to_device(x)
+    m_d, f32 = eng._masses_dev(m)
+    peaks = measured_peaks()
+    for tag, dtype, lanes in (("f32", np.float32, 128), ("f64", np.float64, 64)):
+        stream = eng.pack(pos_d, m_d, f32, n, dtype)
+        ws = eng.workspace(n, n, dtype)
+        for _ in range(3):
+            eng.accel_slab(stream, n, 0, n, 0.01, ws)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            eng.accel_slab(stream, n, 0, n, 0.01, ws)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gi = n * (n - 1.0) / ms / 1e6
+        peak_tf = eng.sm_count * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        out[f"single_system_N{n}_{tag}"] = {"Ginteractions_per_s": round(gi, 1), "ms_per_force_eval": round(ms, 4),
+                                            "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / peak_tf, 4),
+                                            "peak_tflops": round(peak_tf, 2)}
+    return out
+
+
+def bench_single(args, world, rank, local, sharded: bool):
+    import torch
+    from hpc import _cuda, ics
+    from hpc.sharded import ShardedSystem
+    eng = _cuda.get_engine(local)
+    n = args.bodies
+    dtype = np.float64 if args.dtype == "f64" else np.float32
+    eps = 0.01 if n <= 16384 else 1e-3
+    x, v, m = ics.plummer_ic(n, seed=7)
+    sysm = ShardedSystem(x, v, m, dt=1e-3, softening=eps, dtype=dtype, device=local,
+                         world=world if sharded else 1, rank=rank if sharded else 0)
+    launches0 = eng.launches
+
+    def step():
+        sysm.advance(args.sim_steps)
+
+    with ClockSampler(local) as clk:
+        secs = time_steps(step, args.steps, args.warmup, world)
+    launches = (eng.launches - launches0) * args.steps // (args.steps + args.warmup)
+    replicas = 1 if sharded else world
+    inter_step = args.sim_steps * n * (n - 1.0)
+    value = replicas * args.steps * inter_step / secs / 1e9
+    peaks = measured_peaks()
+    lanes = 64 if dtype == np.float64 else 128
+    peak_tf = eng.sm_count * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12 * world
+    ach = value * 1e9 * FLOPS_PER_INTERACTION / 1e12
+
+    # e2e: public API with host arrays (upload + run + download of the final state)
+    from hpc.nbody import NBodySimulator
+    e2e = None
+    if not sharded and rank == 0:
+        np.random.seed(0)
+        sim = NBodySimulator.__new__(NBodySimulator)
+        sim.n_particles, sim.box_size, sim.dt, sim.softening = n, 1.0, 1e-3, eps
+        sim.use_barnes_hut, sim.theta, sim.seed, sim.dtype, sim.device = False, 0.5, None, np.dtype(dtype), local
+        sim.positions, sim.velocities, sim.masses = x.copy(), v.copy(), m.copy()
+        sim.time, sim.step_count, sim.history = 0.0, 0, []
+        sim.accelerations = sim._compute_accelerations()
+        sim.run(args.sim_steps, save_interval=args.sim_steps, verbose=False)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            sim.run(args.sim_steps, save_interval=args.sim_steps, verbose=False)
+        es = time.perf_counter() - t0
+        e2e = {"value": round(reps * inter_step / es / 1e9, 2), "unit": UNIT,
+               "h2d_bytes_per_step": int(3 * x.nbytes + m.nbytes), "d2h_bytes_per_step": int(3 * x.nbytes * 2),
+               "api": "NBodySimulator.run(host state) -> list of host state dicts"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nc = min(n, 16384)
+        v_cpu, s_cpu, cores = cpu_single_sample(nc)
+        cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"one force evaluation at N={nc}, all threads, {s_cpu:.2f} s"}
+    return {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 4), "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"single system N={n} Plummer, {args.sim_steps} leapfrog steps per bench step",
+                   "softening": eps, "l2": "compute-bound; working set " + f"{n * 16 / 1e6:.1f} MB is L2-resident by design",
+                   "parallelism": (f"i-slab over {world} ranks, one all-gather of positions per step" if sharded
+                                   else f"{world} independent replica(s)")},
+        "sim_steps_per_s": round(replicas * args.steps * args.sim_steps / secs, 2),
+        "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"kernel": f"force_{args.dtype}_kernel", "bound": "fp64" if dtype == np.float64 else "fp32",
+                     "achieved": round(ach, 2), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
+                     "frac": round(ach / peak_tf, 4), "traffic": None,
+                     "peak_source": f"{world} x {eng.sm_count} SMs x {lanes} lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz"},
+        "cpu_baseline": cpu, "clocks": clk.summary(),
+    }
+
+
+def profile_summary() -> dict:
+    p = ROOT / "profiles" / "summary.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return {}
+    return {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ensemble", choices=["ensemble", "single", "sharded"])
+    ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
+    ap.add_argument("--bodies", type=int, default=65536)
+    ap.add_argument("--sim-steps", type=int, default=10, help="leapfrog steps per bench step (single/sharded)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.dtype is None:
+        args.dtype = "f64" if args.workload == "ensemble" else "f32"
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world, rank, local = dist_setup(args.gpus)
+    if args.workload == "ensemble":
+        line = bench_ensemble(args, world, rank, local)
+    else:
+        line = bench_single(args, world, rank, local, sharded=(args.workload == "sharded"))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,16 +2,27 @@
 //
 // Replaces the process pool of the data-generation script, reference
 // scripts/generate_data.py:32-58,142-149: there each worker builds one NBodySimulator and calls
-// run(n_steps) (src/hpc/nbody.py:220-248), i.e. n_steps x [step() + get_state()].  Here one CTA
-// owns one system for a range of steps: positions + G*m live in shared memory, every body has
-// `parts` threads that each sum a contiguous j range (partials combined in ascending part order),
-// the body's owner thread keeps (x, v, a) in registers, applies the kicks and the drift and
-// streams the snapshot rows (x_k, v_k, a_k) straight to HBM in the reference's (T+1, N, 3) layout.
+// run(n_steps) (src/hpc/nbody.py:220-248), i.e. n_steps x [step() + get_state()].
+//
+// One CTA owns one system for a range of steps; the whole state lives in shared memory:
+//   pos   N x {x,y,z,G*m}      read by every thread in the force phase (broadcast LDS.128)
+//   vel, acc   3N each          the integrator's state, (body, component) order = API order
+//   part  parts x 3N            force partials, one slab per j-part
+//   stage 3 x 3N                the snapshot row (x_k, v_k, a_k) waiting to be streamed out
+// A step is two phases separated by two CTA barriers:
+//   F  every thread owns TWO bodies (r, r + rows) and one of `parts` contiguous j ranges: 2
+//      independent interaction chains per loaded j.  Before its force loop the thread streams its
+//      share of the previous step's snapshot row from `stage` to HBM -- consecutive 8-byte words,
+//      fully coalesced, in the reference's (T+1, N, 3) layout, overlapped with the arithmetic.
+//   I  the 3N (body, component) scalars are spread over all threads: partials added in ascending
+//      part order, closing kick, snapshot into `stage`, next opening kick and drift.
+// For N = 200 this is 100 rows x 5 parts = 500 threads -> 16 warps, four per scheduler, two CTAs
+// per SM: the four FP64 pipes of an SM carry equal load (13-warp CTAs lost 20% to that skew).
 //
 // Scheduling.  The grid is persistent: at most (resident CTAs per SM) x (SM count) CTAs.  If the
 // ensemble fits (B <= grid) every CTA runs its system start to finish.  Otherwise the run is cut
-// into step chunks and CTAs draw (chunk, system) tickets from a global counter, chunk-major; the
-// state of a system is handed from chunk to chunk through the in/out state arrays and a per-system
+// into short step chunks and CTAs draw (chunk, system) tickets from a global counter, chunk-major;
+// a system's state is handed from chunk to chunk through the in/out state arrays and a per-system
 // progress word.  A ticket's predecessor always has a lower ticket number, hence a CTA that is
 // already running, so the waits cannot deadlock.  This removes the 300-systems-on-148-SMs tail.
 #include "nb_common.cuh"
@@ -63,133 +74,163 @@ struct EnsembleArgs {
     double* out_v;
     double* out_a;
     int n_snap_total, snap_offset;
-    int parts;        // threads per body
-    int chunk_steps;  // steps per ticket (dynamic mode)
+    int rows;         // threads per part; a thread owns bodies r and r + rows
+    int parts;        // j-parts
+    int chunk_steps;  // steps per ticket (ticket mode)
     int n_chunks;
-    int* ticket;      // dynamic mode: global ticket counter, zero on entry
-    int* progress;    // dynamic mode: per-system count of finished chunks, zero on entry
+    int* ticket;      // ticket mode: global ticket counter, zero on entry
+    int* progress;    // ticket mode: per-system count of finished chunks, zero on entry
 };
 
-// Advance system b from step k_begin (state as stored in args.x/v/a) to k_end.
-// k_begin == 0 additionally handles the initial acceleration and the initial snapshot.
-template <typename T, bool kZeroEps>
-__device__ __forceinline__ void advance_system(const EnsembleArgs& g, int b, int k_begin, int k_end,
-                                               typename Vec4<T>::type* posm, T* part_acc) {
-    using V4 = typename Vec4<T>::type;
-    const int N = g.N;
-    const int tid = threadIdx.x;
-    const int q = tid / N;       // which j-part this thread sums
-    const int i = tid - q * N;   // which body
-    const bool active = q < g.parts;
-    const bool owner = active && q == 0;
-    const int jb = active ? (int)(((long)q * N) / g.parts) : 0;
-    const int je = active ? (int)(((long)(q + 1) * N) / g.parts) : 0;
-    const size_t row = (size_t)N * 3;
-    const size_t sbase = (size_t)b * row;
-    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
+template <typename T>
+struct SystemSmem {
+    typename Vec4<T>::type* pos;
+    T* vel;
+    T* acc;
+    T* part;
+    T* stage;  // x | v | a, 3N each
+};
 
-    T x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, a[3] = {0, 0, 0};
-    __syncthreads();  // previous system's readers are done with posm / part_acc
-    if (owner) {
-        const char* mb = static_cast<const char*>(g.masses);
-        const size_t mi = (size_t)b * g.mass_stride + i;
-        const double m = g.masses_are_f32 ? (double)reinterpret_cast<const float*>(mb)[mi]
-                                          : reinterpret_cast<const double*>(mb)[mi];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            // L2 loads: in ticket mode another SM may have written this state a chunk ago
-            x[c] = (T)__ldcg(&g.x[sbase + (size_t)i * 3 + c]);
-            v[c] = (T)__ldcg(&g.v[sbase + (size_t)i * 3 + c]);
-            a[c] = (T)__ldcg(&g.a[sbase + (size_t)i * 3 + c]);
-        }
-        V4 p;
-        p.x = x[0]; p.y = x[1]; p.z = x[2];
-        p.w = (T)(kG * m);  // G * masses[j], nbody.py:57
-        posm[i] = p;
-    }
-    __syncthreads();
+template <typename T>
+__host__ __device__ inline size_t ensemble_smem_bytes(int N, int parts) {
+    return (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(2 + parts + 3) * 3 * N * sizeof(T);
+}
 
-    for (int k = k_begin; k <= k_end; ++k) {
-        const bool need_force = (k > 0) || g.compute_a0;
-        const bool entry_state = (k == k_begin) && (k_begin > 0);  // (x,v,a) of step k_begin were finished by the previous chunk
-        if (need_force && !entry_state) {
-            T fx = 0, fy = 0, fz = 0;
-            if (active) {
-                const V4 me = posm[i];
-#pragma unroll 4
-                for (int j = jb; j < je; ++j) {
-                    const V4 pj = posm[j];
-                    pair_any<kZeroEps>(me.x, me.y, me.z, pj.x, pj.y, pj.z, pj.w, eps2, fx, fy, fz);
-                }
-                if (q > 0) {
-                    T* pa = part_acc + (size_t)(q - 1) * 3 * N;
-                    pa[i] = fx; pa[N + i] = fy; pa[2 * N + i] = fz;
-                }
-            }
-            __syncthreads();
-            if (owner) {
-                for (int p = 1; p < g.parts; ++p) {
-                    const T* pa = part_acc + (size_t)(p - 1) * 3 * N;
-                    fx += pa[i]; fy += pa[N + i]; fz += pa[2 * N + i];
-                }
-                a[0] = fx; a[1] = fy; a[2] = fz;
-            }
-        }
-        if (owner) {
-            if (k > 0 && !entry_state) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = mul_add_unfused(half_dt, a[c], v[c]);  // closing kick, nbody.py:214
-            }
-            // snapshot rows: get_state() before the loop and every save_interval steps, nbody.py:235,240-241
-            long srow = -1;
-            if (k == 0) {
-                if (g.write_initial) srow = g.snap_offset;
-            } else if (!entry_state && (k % g.save_interval) == 0) {
-                srow = g.snap_offset + (g.write_initial ? 1 : 0) + (k / g.save_interval - 1);
-            }
-            if (srow >= 0 && g.out_x) {
-                const size_t o = ((size_t)b * g.n_snap_total + (size_t)srow) * row + (size_t)i * 3;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    g.out_x[o + c] = (double)x[c];
-                    g.out_v[o + c] = (double)v[c];
-                    g.out_a[o + c] = (double)a[c];
-                }
-            }
-            if (k < k_end) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    v[c] = mul_add_unfused(half_dt, a[c], v[c]);  // opening kick, nbody.py:205
-                    x[c] = mul_add_unfused(dt, v[c], x[c]);       // drift, nbody.py:208
-                }
-                V4 p = posm[i];
-                p.x = x[0]; p.y = x[1]; p.z = x[2];
-                posm[i] = p;
-            }
-        }
-        __syncthreads();
-    }
-    if (owner) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            g.x[sbase + (size_t)i * 3 + c] = (double)x[c];
-            g.v[sbase + (size_t)i * 3 + c] = (double)v[c];
-            g.a[sbase + (size_t)i * 3 + c] = (double)a[c];
-        }
-        __threadfence();  // publish before the progress word is advanced (ticket mode)
+// Stream the staged snapshot row to HBM: 3 x 3N consecutive doubles, coalesced.
+template <typename T>
+__device__ __forceinline__ void flush_stage(const EnsembleArgs& g, const SystemSmem<T>& s, int b, long srow) {
+    const int n3 = 3 * g.N;
+    const size_t o = ((size_t)b * g.n_snap_total + (size_t)srow) * n3;
+    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+        g.out_x[o + idx] = (double)s.stage[idx];
+        g.out_v[o + idx] = (double)s.stage[n3 + idx];
+        g.out_a[o + idx] = (double)s.stage[2 * n3 + idx];
     }
 }
 
+// Advance system b from step k_begin (state as stored in g.x/v/a) to k_end.
+// k_begin == 0 additionally handles the initial acceleration and the initial snapshot.
 template <typename T, bool kZeroEps>
-__global__ void __launch_bounds__(1024) ensemble_kernel(const EnsembleArgs g) {
+__device__ __forceinline__ void advance_system(const EnsembleArgs& g, int b, int k_begin, int k_end,
+                                               const SystemSmem<T>& s) {
+    using V4 = typename Vec4<T>::type;
+    const int N = g.N, n3 = 3 * N;
+    const int tid = threadIdx.x;
+    const int q = tid / g.rows;      // j-part of this thread
+    const int r = tid - q * g.rows;  // row: bodies r and r + rows
+    const bool active = q < g.parts;
+    const int i0 = r, i1 = r + g.rows;
+    const bool has1 = i1 < N;
+    const int jb = active ? (int)(((long)q * N) / g.parts) : 0;
+    const int je = active ? (int)(((long)(q + 1) * N) / g.parts) : 0;
+    const size_t sbase = (size_t)b * n3;
+    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
+    T* pos_s = reinterpret_cast<T*>(s.pos);
+
+    __syncthreads();  // the previous system's readers are done with the shared state
+    for (int idx = tid; idx < n3; idx += blockDim.x) {
+        // L2 loads: in ticket mode another SM wrote this state a chunk ago
+        const int i = idx / 3, c = idx - 3 * i;
+        pos_s[4 * i + c] = (T)__ldcg(&g.x[sbase + idx]);
+        s.vel[idx] = (T)__ldcg(&g.v[sbase + idx]);
+        s.acc[idx] = (T)__ldcg(&g.a[sbase + idx]);
+    }
+    for (int i = tid; i < N; i += blockDim.x) {
+        const size_t mi = (size_t)b * g.mass_stride + i;
+        const double m = g.masses_are_f32 ? (double)static_cast<const float*>(g.masses)[mi]
+                                          : static_cast<const double*>(g.masses)[mi];
+        pos_s[4 * i + 3] = (T)(kG * m);  // G * masses[j], nbody.py:57
+    }
+    __syncthreads();
+
+    long pending = -1;  // snapshot row staged but not yet streamed out (uniform across the CTA)
+    for (int k = k_begin; k <= k_end; ++k) {
+        const bool entry_state = (k == k_begin) && (k_begin > 0);  // (x,v,a)_k were finished by the previous chunk
+        const bool do_force = !entry_state && ((k > 0) || g.compute_a0);
+        const bool do_close = !entry_state && k > 0;
+        const bool do_open = k < k_end;
+        long srow = -1;  // get_state() before the loop and every save_interval steps, nbody.py:235,240-241
+        if (g.out_x && !entry_state) {
+            if (k == 0) {
+                if (g.write_initial) srow = g.snap_offset;
+            } else if ((k % g.save_interval) == 0) {
+                srow = g.snap_offset + (g.write_initial ? 1 : 0) + (k / g.save_interval - 1);
+            }
+        }
+        // ---- phase F -----------------------------------------------------------------------------
+        if (pending >= 0) {
+            flush_stage<T>(g, s, b, pending);
+            pending = -1;
+        }
+        if (do_force) {
+            if (active) {
+                const V4 me0 = s.pos[i0];
+                const V4 me1 = s.pos[has1 ? i1 : i0];
+                T ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
+#pragma unroll 2
+                for (int j = jb; j < je; ++j) {
+                    const V4 pj = s.pos[j];
+                    pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
+                    pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, eps2, ax1, ay1, az1);
+                }
+                T* pa = s.part + (size_t)q * n3;
+                pa[3 * i0 + 0] = ax0; pa[3 * i0 + 1] = ay0; pa[3 * i0 + 2] = az0;
+                if (has1) { pa[3 * i1 + 0] = ax1; pa[3 * i1 + 1] = ay1; pa[3 * i1 + 2] = az1; }
+            }
+            __syncthreads();
+        }
+        // ---- phase I -----------------------------------------------------------------------------
+        for (int idx = tid; idx < n3; idx += blockDim.x) {
+            const int i = idx / 3, c = idx - 3 * i;
+            T a = s.acc[idx];
+            if (do_force) {
+                a = s.part[idx];
+                for (int p = 1; p < g.parts; ++p) a += s.part[(size_t)p * n3 + idx];
+                s.acc[idx] = a;
+            }
+            T v = s.vel[idx];
+            T x = pos_s[4 * i + c];
+            if (do_close) v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
+            if (srow >= 0) {
+                s.stage[idx] = x;
+                s.stage[n3 + idx] = v;
+                s.stage[2 * n3 + idx] = a;
+            }
+            if (do_open) {
+                v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
+                x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
+                pos_s[4 * i + c] = x;
+            }
+            s.vel[idx] = v;
+        }
+        pending = srow;
+        __syncthreads();
+    }
+    if (pending >= 0) flush_stage<T>(g, s, b, pending);
+    for (int idx = tid; idx < n3; idx += blockDim.x) {
+        const int i = idx / 3, c = idx - 3 * i;
+        g.x[sbase + idx] = (double)pos_s[4 * i + c];
+        g.v[sbase + idx] = (double)s.vel[idx];
+        g.a[sbase + idx] = (double)s.acc[idx];
+    }
+    __threadfence();  // publish before the progress word is advanced (ticket mode)
+}
+
+template <typename T, bool kZeroEps, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ensemble_kernel(const EnsembleArgs g) {
     using V4 = typename Vec4<T>::type;
     extern __shared__ __align__(16) char smem[];
-    V4* posm = reinterpret_cast<V4*>(smem);
-    T* part_acc = reinterpret_cast<T*>(smem + (size_t)g.N * sizeof(V4));
+    const int n3 = 3 * g.N;
+    SystemSmem<T> s;
+    s.pos = reinterpret_cast<V4*>(smem);
+    s.vel = reinterpret_cast<T*>(smem + (size_t)g.N * sizeof(V4));
+    s.acc = s.vel + n3;
+    s.part = s.acc + n3;
+    s.stage = s.part + (size_t)g.parts * n3;
     __shared__ int s_ticket;
 
     if (g.ticket == nullptr) {  // static: one CTA per system, start to finish
-        for (int b = blockIdx.x; b < g.B; b += gridDim.x) advance_system<T, kZeroEps>(g, b, 0, g.n_steps, posm, part_acc);
+        for (int b = blockIdx.x; b < g.B; b += gridDim.x) advance_system<T, kZeroEps>(g, b, 0, g.n_steps, s);
         return;
     }
     const int n_tickets = g.n_chunks * g.B;
@@ -204,14 +245,14 @@ __global__ void __launch_bounds__(1024) ensemble_kernel(const EnsembleArgs g) {
         if (chunk > 0) {
             if (threadIdx.x == 0) {
                 volatile int* flag = g.progress + b;
-                while (*flag < chunk) __nanosleep(64);
+                while (*flag < chunk) __nanosleep(32);
                 __threadfence();
             }
             __syncthreads();
         }
         const int k0 = chunk * g.chunk_steps;
         const int k1 = min(k0 + g.chunk_steps, g.n_steps);
-        advance_system<T, kZeroEps>(g, b, k0, k1, posm, part_acc);
+        advance_system<T, kZeroEps>(g, b, k0, k1, s);
         __syncthreads();
         if (threadIdx.x == 0) atomicExch(g.progress + b, chunk + 1);
     }
@@ -244,15 +285,22 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     g.n_steps = n_steps; g.save_interval = save_interval; g.compute_a0 = compute_a0; g.write_initial = write_initial;
     g.out_x = out_x; g.out_v = out_v; g.out_a = out_a;
     g.n_snap_total = n_snap_total; g.snap_offset = snap_offset;
-    // threads per body: fill about 416 threads per CTA (13 warps), at most 8 parts
-    int parts = 416 / N;
+    // two bodies per thread; as many j-parts as fit in 512 threads (at most 8)
+    g.rows = ceil_div(N, 2);
+    int parts = 512 / g.rows;
     if (parts < 1) parts = 1;
     if (parts > 8) parts = 8;
+    if (parts > N) parts = N;
     g.parts = parts;
-    const int threads = round_up(N * parts, 32);
-    const size_t smem = (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(parts - 1) * 3 * N * sizeof(T);
+    const int threads = round_up(g.rows * parts, 32);
+    const size_t smem = ensemble_smem_bytes<T>(N, parts);
     const bool zero = !((T)g.eps2 > T(0));
-    auto kern = zero ? ensemble_kernel<T, true> : ensemble_kernel<T, false>;
+    // up to 512 threads: two CTAs per SM on a 64-register budget; more rows: one CTA per SM
+    void (*kern)(const EnsembleArgs);
+    if (threads <= 512 && 2 * smem <= 200 * 1024)
+        kern = zero ? ensemble_kernel<T, true, 512, 2> : ensemble_kernel<T, false, 512, 2>;
+    else
+        kern = zero ? ensemble_kernel<T, true, 1024, 1> : ensemble_kernel<T, false, 1024, 1>;
     NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, dev = 0, sms = 0;
     NB_CUDA_OK(cudaGetDevice(&dev));
@@ -262,13 +310,14 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     const int resident = per_sm * sms;
     g.ticket = nullptr; g.progress = nullptr; g.chunk_steps = n_steps; g.n_chunks = 1;
     int grid = B < resident ? B : resident;
-    if (B > resident && n_steps >= 16) {
-        // ticket mode: about a dozen tickets per resident CTA keeps the tail under a few percent
+    if (B > resident && n_steps >= 8) {
+        // ticket mode: ~48 tickets per resident CTA (tail and hand-over waits of a percent or two),
+        // chunks of at least 4 steps (state reload amortised)
         NB_REQUIRE(ws && ws_bytes >= nb_ensemble_workspace_bytes(B), "ensemble workspace too small: %zu < %zu",
                    ws_bytes, nb_ensemble_workspace_bytes(B));
-        int want = ceil_div(12 * resident, B);
+        const int want = ceil_div(48 * resident, B);
         int steps = ceil_div(n_steps, want);
-        if (steps < 8) steps = 8;
+        if (steps < 4) steps = 4;
         g.chunk_steps = steps;
         g.n_chunks = ceil_div(n_steps, steps);
         g.ticket = static_cast<int*>(ws);

@@ -204,11 +204,15 @@ class Engine:
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes
 
     # ---- device-level operations (tensors in, tensors out; used by nbody.py and sharded.py) ----
-    def pack(self, pos_dev, masses_dev, masses_f32: int, n: int, dtype):
-        """API-layout positions (n,3) float64 + masses -> stream-layout tensor of `dtype`."""
+    def pack(self, pos_dev, masses_dev, masses_f32: int, n: int, dtype, out=None):
+        """API-layout positions (n,3) float64 + masses -> stream-layout tensor of `dtype`.
+
+        `out`: optional preallocated stream (at least padded_bodies(n)*4 elements; the kernel writes
+        exactly that many)."""
         torch = _torch()
         sfx = self._suffix(dtype)
-        stream = torch.empty(self.padded_bodies(n) * 4, dtype=self._tdtype(dtype), device=self.device)
+        stream = out if out is not None else torch.empty(self.padded_bodies(n) * 4, dtype=self._tdtype(dtype),
+                                                         device=self.device)
         self._check(getattr(self.lib, f"nb_pack_{sfx}")(self._p(pos_dev), self._p(masses_dev), masses_f32, n,
                                                          self._p(stream), self._stream()))
         self.launches += 1

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Small fixed workload for ncu captures: one launch of each hot kernel (development aid)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "nbody-gnn-hpc_b200"))
+from hpc import _cuda, ics  # noqa: E402
+
+which = sys.argv[1:] or ["f32", "f64", "ens"]
+eng = _cuda.get_engine()
+if "f32" in which or "f64" in which:
+    n = 65536
+    x, v, m = ics.plummer_ic(n, seed=7)
+    pos_d = eng.to_device(x)
+    m_d, f32 = eng._masses_dev(m)
+    for tag, dtype in (("f32", np.float32), ("f64", np.float64)):
+        if tag in which:
+            stream = eng.pack(pos_d, m_d, f32, n, dtype)
+            ws = eng.workspace(n, n, dtype)
+            for _ in range(2):
+                eng.accel_slab(stream, n, 0, n, 0.01, ws)
+            torch.cuda.synchronize()
+if "ens" in which:
+    B, steps = 296, 50
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=42)
+    x, v = eng.to_device(x0), eng.to_device(v0)
+    a = torch.zeros_like(x)
+    m_d, f32 = eng._masses_dev(m32)
+    ox = torch.empty((B, steps + 1, 200, 3), dtype=torch.float64, device=eng.device)
+    ov, oa = torch.empty_like(ox), torch.empty_like(ox)
+    for _ in range(2):
+        eng.ensemble_device(x, v, a, m_d, f32, 0, B, 200, 1e-3, 1e-9, steps, 1, np.float64, True, True, ox, ov, oa,
+                            steps + 1, 0)
+    torch.cuda.synchronize()
+print("ok")
