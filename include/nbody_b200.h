@@ -150,6 +150,11 @@ int nb_ensemble_f32(double* x, double* v, double* a, const void* masses, int mas
                     double* out_x, double* out_v, double* out_a, int n_snap_total, int snap_offset,
                     void* workspace, size_t workspace_bytes, nb_stream_t s);
 
+/* Strided device -> host copy of snapshot rows (height rows of width bytes; pitches in bytes), so the
+ * rows of one step-chunk of every system can drain to pinned host memory while the next chunk runs. */
+int nb_copy_rows_d2h_async(void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width,
+                           size_t height, nb_stream_t s);
+
 /* ---- K4: energy ---------------------------------------------------------------------------------
  * Replaces compute_total_energy, reference src/hpc/nbody.py:101-130 (and the per-step energy of
  * src/utils/metrics.py:62-109): kinetic and potential energy contributed by rows [i0, i0+n_i) --

@@ -110,9 +110,9 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 // One softened pair interaction in fp64, accumulating into (ax, ay, az).
 //   reference: src/hpc/nbody.py:47-60   r2 = dx^2+dy^2+dz^2+eps^2; factor = G*m_j / (sqrt(r2)*r2)
 // gm_j = G*m_j is folded on the host side of the kernel.  factor = gm * r2^(-3/2) is formed as
-//   y0 = seed(r2),  e = 1 - r2*y0^2,  r2^(-3/2) = y0^3 * (1 + 3/2 e + 15/8 e^2 + O(e^3)),
+//   y0 = seed(r2),  e = 1 - r2*y0^2  (one FMA on the rounded square),  r2^(-3/2) = y0^3 * (1 + 3/2 e + 15/8 e^2 + O(e^3)),
 // i.e. one third-order correction of the cubed seed: truncation 35/16 e^3 < 2^-64 for |e| < 2^-21.
-// 17 FP64-pipe operations + 1 MUFU per interaction.
+// 16 FP64-pipe operations + 1 MUFU per interaction.
 template <bool kZeroEps>
 __device__ __forceinline__ void pair_f64(double xi, double yi, double zi, double xj, double yj, double zj, double gmj,
                                          double eps2, double& ax, double& ay, double& az) {
@@ -124,9 +124,8 @@ __device__ __forceinline__ void pair_f64(double xi, double yi, double zi, double
     r2 = fma(dz, dz, r2);
     double y0 = rsqrt_seed(r2);
     if (kZeroEps) y0 = (r2 > 0.0) ? y0 : 0.0;  // eps == 0: the i == j term (and exact overlaps) contribute 0
-    const double t = r2 * y0;
-    const double e = fma(-t, y0, 1.0);
     const double y2 = y0 * y0;
+    const double e = fma(-r2, y2, 1.0);  // y2 carries one rounding (2^-53): 1.5 * 2^-53 relative in f
     const double g = gmj * y0;
     const double w = y2 * g;
     const double p = fma(1.875, e, 1.5);

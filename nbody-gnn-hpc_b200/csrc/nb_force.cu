@@ -14,7 +14,7 @@
 //
 // float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
 // (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
-// float64 inner loop: pair_f64() in nb_common.cuh, 17 FP64-pipe operations + 1 MUFU.RSQ64H.
+// float64 inner loop: pair_f64() in nb_common.cuh, 16 FP64-pipe operations + 1 MUFU.RSQ64H.
 #include "nb_common.cuh"
 
 namespace nb {
@@ -89,7 +89,7 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
     auto consume = [&](const char* tile, int bytes) {
         const float4* __restrict__ t = reinterpret_cast<const float4*>(tile);
         const int n_pairs = bytes >> 5;
-#pragma unroll 4
+#pragma unroll 2
         for (int jp = 0; jp < n_pairs; ++jp) {
             const float4 A = t[2 * jp];      // x0 x1 y0 y1
             const float4 B = t[2 * jp + 1];  // z0 z1 gm0 gm1

@@ -255,3 +255,15 @@ int nbh_total_energy(const double* pos, const double* vel, const void* masses, i
 }
 
 }  // extern "C"
+
+// Strided device -> host copy of a block of snapshot rows: `height` rows of `width` bytes, row starts
+// `spitch` / `dpitch` bytes apart.  Lets the host side drain the rows of one step-chunk of every
+// system (a (B, rows, N, 3) sub-block of the (B, T+1, N, 3) stacks) while the next chunk computes.
+extern "C" int nb_copy_rows_d2h_async(void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width,
+                                       size_t height, nb_stream_t s) {
+    NB_REQUIRE(dst_host && src_dev && width > 0 && height > 0 && dpitch >= width && spitch >= width,
+               "nb_copy_rows_d2h_async: bad argument");
+    NB_CUDA_OK(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, height, cudaMemcpyDeviceToHost,
+                                 (cudaStream_t)s));
+    return NB_OK;
+}

@@ -60,6 +60,7 @@ _SIGNATURES = {
                               _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
     "nb_ensemble_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
                               _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
+    "nb_copy_rows_d2h_async": (_ci, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "nb_energy_workspace_bytes": (_sz, [_ci, _ci]),
     "nb_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
     "nbh_accel_direct": (_ci, [_vp, _vp, _ci, _ci, _cd, _ci, _vp]),
@@ -364,20 +365,60 @@ class Engine:
             else:
                 a = self.to_device(np.ascontiguousarray(a0, dtype=np.float64))
             m_d, f32 = self._masses_dev(np.ascontiguousarray(m))
-            if snapshots:
-                ox = torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=self.device)
-                ov = torch.empty_like(ox)
-                oa = torch.empty_like(ox)
-            else:
-                ox = ov = oa = None
-            self.ensemble_device(x, v, a, m_d, f32, mass_stride, B, N, dt, softening, n_steps, save_interval, dtype,
-                                 compute_a0=a0 is None, write_initial=True, out_x=ox, out_v=ov, out_a=oa,
-                                 n_snap_total=n_snap, snap_offset=0)
+            if not snapshots:
+                self.ensemble_device(x, v, a, m_d, f32, mass_stride, B, N, dt, softening, n_steps, save_interval,
+                                     dtype, compute_a0=a0 is None, write_initial=False, out_x=None, out_v=None,
+                                     out_a=None, n_snap_total=0, snap_offset=0)
+                return {"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
+                        "final_accelerations": self.to_host(a)}
+            ox = torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=self.device)
+            ov = torch.empty_like(ox)
+            oa = torch.empty_like(ox)
+            host = [torch.empty((B, n_snap, N, 3), dtype=torch.float64, pin_memory=True) for _ in range(3)]
+            # Snapshot volume (72*N bytes per system-step) drains over PCIe several times slower than the
+            # kernel produces it, so the run is cut into step chunks: the rows of chunk c go to pinned host
+            # memory on a copy stream while chunk c+1 computes.  Chunk edges are multiples of save_interval.
+            row_bytes = N * 3 * 8
+            total_bytes = 3 * B * n_snap * row_bytes
+            n_chunks = 1 if total_bytes < (32 << 20) else min(8, max(1, n_steps // save_interval))
+            saves = n_steps // save_interval
+            edges = sorted({(saves * c // n_chunks) * save_interval for c in range(n_chunks)} | {n_steps})
+            if edges[0] != 0:
+                edges.insert(0, 0)
+            if len(edges) == 1:          # n_steps == 0: only the entry state is recorded
+                edges.append(edges[0])
+            compute = torch.cuda.current_stream(self.device)
+            copier = self._copy_stream()
+            copier.wait_stream(compute)
+            row0 = 0
+            for c in range(len(edges) - 1):
+                k0, k1 = edges[c], edges[c + 1]
+                first = c == 0
+                rows = (k1 - k0) // save_interval + (1 if first else 0)
+                self.ensemble_device(x, v, a, m_d, f32, mass_stride, B, N, dt, softening, k1 - k0, save_interval,
+                                     dtype, compute_a0=first and a0 is None, write_initial=first, out_x=ox, out_v=ov,
+                                     out_a=oa, n_snap_total=n_snap, snap_offset=row0)
+                if rows:
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    copier.wait_event(done)
+                    pitch = n_snap * row_bytes
+                    for dev_t, host_t in zip((ox, ov, oa), host):
+                        self._check(self.lib.nb_copy_rows_d2h_async(
+                            ctypes.c_void_p(host_t.data_ptr() + row0 * row_bytes), pitch,
+                            ctypes.c_void_p(dev_t.data_ptr() + row0 * row_bytes), pitch, rows * row_bytes, B,
+                            ctypes.c_void_p(copier.cuda_stream)))
+                row0 += rows
             res = {"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
                    "final_accelerations": self.to_host(a)}
-            if snapshots:
-                res.update(positions=self.to_host(ox), velocities=self.to_host(ov), accelerations=self.to_host(oa))
+            copier.synchronize()
+            res.update(positions=host[0].numpy(), velocities=host[1].numpy(), accelerations=host[2].numpy())
             return res
+
+    def _copy_stream(self):
+        if getattr(self, "_copier", None) is None:
+            self._copier = _torch().cuda.Stream(device=self.device)
+        return self._copier
 
     def energy(self, positions, velocities, masses, softening: float):
         """compute_total_energy (reference nbody.py:101-130) -> (K, U, K+U) Python floats."""
