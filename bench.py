@@ -56,7 +56,7 @@ class ClockSampler:
     BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
     NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks", 0x100: "display_clocks"}
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.01):
         self.index, self.period = index, period_s
         self.samples, self.reasons = [], set()
         self.max_mhz = None
@@ -147,7 +147,7 @@ def run_reference_arm(args) -> None:
     oracle.build()
     cores = oracle.num_threads()
     if args.workload == "ensemble":
-        n_sims = max(2 * cores, 8)
+        n_sims = max(16 * cores, 32)          # ~1 s of wall time, ~16 core-seconds per step
         sample = f"{n_sims} of {ENS_B} simulations x {ENS_N} bodies x {ENS_STEPS} steps per step, {cores} threads"
         fn = lambda: cpu_ensemble_sample(n_sims)      # noqa: E731
         cfg = {"workload": f"datagen ensemble {ENS_B}x{ENS_N}x{ENS_STEPS} fp64 (configs[1])"}

@@ -76,8 +76,9 @@ struct EnsembleArgs {
     int n_snap_total, snap_offset;
     int rows;         // threads per part; a thread owns bodies r and r + rows
     int parts;        // j-parts
-    int chunk_steps;  // steps per ticket (ticket mode)
+    int chunk_steps;  // steps per leftover ticket
     int n_chunks;
+    int home_rounds;  // whole grid-rounds of systems that stay resident in their CTA (0: everything by ticket)
     int* ticket;      // ticket mode: global ticket counter, zero on entry
     int* progress;    // ticket mode: per-system count of finished chunks, zero on entry
 };
@@ -108,28 +109,16 @@ __device__ __forceinline__ void flush_stage(const EnsembleArgs& g, const SystemS
     }
 }
 
-// Advance system b from step k_begin (state as stored in g.x/v/a) to k_end.
-// k_begin == 0 additionally handles the initial acceleration and the initial snapshot.
-template <typename T, bool kZeroEps>
-__device__ __forceinline__ void advance_system(const EnsembleArgs& g, int b, int k_begin, int k_end,
-                                               const SystemSmem<T>& s) {
-    using V4 = typename Vec4<T>::type;
+// Global state of system b -> shared memory (synchronised state of some step k).
+template <typename T>
+__device__ __forceinline__ void load_state(const EnsembleArgs& g, int b, const SystemSmem<T>& s) {
     const int N = g.N, n3 = 3 * N;
     const int tid = threadIdx.x;
-    const int q = tid / g.rows;      // j-part of this thread
-    const int r = tid - q * g.rows;  // row: bodies r and r + rows
-    const bool active = q < g.parts;
-    const int i0 = r, i1 = r + g.rows;
-    const bool has1 = i1 < N;
-    const int jb = active ? (int)(((long)q * N) / g.parts) : 0;
-    const int je = active ? (int)(((long)(q + 1) * N) / g.parts) : 0;
     const size_t sbase = (size_t)b * n3;
-    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
     T* pos_s = reinterpret_cast<T*>(s.pos);
-
     __syncthreads();  // the previous system's readers are done with the shared state
     for (int idx = tid; idx < n3; idx += blockDim.x) {
-        // L2 loads: in ticket mode another SM wrote this state a chunk ago
+        // L2 loads: another SM may have written this state a chunk ago
         const int i = idx / 3, c = idx - 3 * i;
         pos_s[4 * i + c] = (T)__ldcg(&g.x[sbase + idx]);
         s.vel[idx] = (T)__ldcg(&g.v[sbase + idx]);
@@ -142,6 +131,40 @@ __device__ __forceinline__ void advance_system(const EnsembleArgs& g, int b, int
         pos_s[4 * i + 3] = (T)(kG * m);  // G * masses[j], nbody.py:57
     }
     __syncthreads();
+}
+
+// Shared memory -> global state of system b, published for other CTAs.
+template <typename T>
+__device__ __forceinline__ void store_state(const EnsembleArgs& g, int b, const SystemSmem<T>& s) {
+    const int n3 = 3 * g.N;
+    const size_t sbase = (size_t)b * n3;
+    const T* pos_s = reinterpret_cast<const T*>(s.pos);
+    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+        const int i = idx / 3, c = idx - 3 * i;
+        g.x[sbase + idx] = (double)pos_s[4 * i + c];
+        g.v[sbase + idx] = (double)s.vel[idx];
+        g.a[sbase + idx] = (double)s.acc[idx];
+    }
+    __threadfence();  // visible before a progress word is advanced
+}
+
+// Advance the system held in shared memory from step k_begin to k_end (synchronised state in, synchronised
+// state out).  k_begin == 0 additionally handles the initial acceleration and the initial snapshot.
+template <typename T, bool kZeroEps>
+__device__ __forceinline__ void run_steps(const EnsembleArgs& g, int b, int k_begin, int k_end,
+                                          const SystemSmem<T>& s) {
+    using V4 = typename Vec4<T>::type;
+    const int N = g.N, n3 = 3 * N;
+    const int tid = threadIdx.x;
+    const int q = tid / g.rows;      // j-part of this thread
+    const int r = tid - q * g.rows;  // row: bodies r and r + rows
+    const bool active = q < g.parts;
+    const int i0 = r, i1 = r + g.rows;
+    const bool has1 = i1 < N;
+    const int jb = active ? (int)(((long)q * N) / g.parts) : 0;
+    const int je = active ? (int)(((long)(q + 1) * N) / g.parts) : 0;
+    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
+    T* pos_s = reinterpret_cast<T*>(s.pos);
 
     long pending = -1;  // snapshot row staged but not yet streamed out (uniform across the CTA)
     for (int k = k_begin; k <= k_end; ++k) {
@@ -207,13 +230,7 @@ __device__ __forceinline__ void advance_system(const EnsembleArgs& g, int b, int
         __syncthreads();
     }
     if (pending >= 0) flush_stage<T>(g, s, b, pending);
-    for (int idx = tid; idx < n3; idx += blockDim.x) {
-        const int i = idx / 3, c = idx - 3 * i;
-        g.x[sbase + idx] = (double)pos_s[4 * i + c];
-        g.v[sbase + idx] = (double)s.vel[idx];
-        g.a[sbase + idx] = (double)s.acc[idx];
-    }
-    __threadfence();  // publish before the progress word is advanced (ticket mode)
+    __syncthreads();  // stage and state are quiescent for whoever comes next
 }
 
 template <typename T, bool kZeroEps, int kMaxThreads, int kMinBlocks>
@@ -227,34 +244,102 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ensemble_kernel(const
     s.acc = s.vel + n3;
     s.part = s.acc + n3;
     s.stage = s.part + (size_t)g.parts * n3;
-    __shared__ int s_ticket;
+    __shared__ int s_claim;
 
-    if (g.ticket == nullptr) {  // static: one CTA per system, start to finish
-        for (int b = blockIdx.x; b < g.B; b += gridDim.x) advance_system<T, kZeroEps>(g, b, 0, g.n_steps, s);
-        return;
-    }
-    const int n_tickets = g.n_chunks * g.B;
-    for (;;) {
+    // Home systems: CTA c owns systems c, c + grid, ... (whole rounds of the grid) and keeps each one in
+    // shared memory from its first step to its last.  Leftover systems (B mod grid of them) are advanced
+    // chunk by chunk by whichever CTA claims the next (chunk, system) ticket at one of its own chunk
+    // boundaries: it parks its home system in global memory, runs the stolen chunk, and takes its home
+    // system back.  Every CTA steals at most `steal_budget` chunks, which spreads the leftover work evenly.
+    const int grid = gridDim.x;
+    const int home_rounds = g.home_rounds;
+    const int b_home = home_rounds * grid;
+    const int n_left = g.B - b_home;
+    const int n_tickets = n_left * g.n_chunks;
+    const int steal_budget = n_left ? (n_tickets + grid - 1) / grid : 0;
+    int steals = 0;
+
+    // Claim the next leftover ticket if its predecessor chunk is finished (non-blocking unless `block`).
+    auto claim = [&](bool block) -> int {
         __syncthreads();
-        if (threadIdx.x == 0) s_ticket = atomicAdd(g.ticket, 1);
-        __syncthreads();
-        const int t = s_ticket;
-        if (t >= n_tickets) break;
-        const int chunk = t / g.B;
-        const int b = t - chunk * g.B;
-        if (chunk > 0) {
-            if (threadIdx.x == 0) {
-                volatile int* flag = g.progress + b;
-                while (*flag < chunk) __nanosleep(32);
-                __threadfence();
+        if (threadIdx.x == 0) {
+            int got = -1;
+            if (block) {
+                // unconditional draw (atomics pipeline at L2; a CAS loop would serialise 296 CTAs), then wait
+                // for the predecessor chunk: it holds a lower ticket, so some running CTA is executing it
+                const int t = atomicAdd(g.ticket, 1);
+                if (t < n_tickets) {
+                    const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
+                    if (chunk > 0) {
+                        volatile int* flag = g.progress + bl;
+                        while (*flag < chunk) __nanosleep(32);
+                    }
+                    got = t;
+                }
+            } else
+            for (;;) {
+                const int t = *reinterpret_cast<volatile int*>(g.ticket);
+                if (t >= n_tickets) break;
+                const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
+                const bool ready = chunk == 0 || *reinterpret_cast<volatile int*>(g.progress + bl) >= chunk;
+                if (ready) {
+                    if (atomicCAS(g.ticket, t, t + 1) == t) { got = t; break; }
+                } else if (!block) {
+                    break;
+                } else {
+                    __nanosleep(64);
+                }
             }
-            __syncthreads();
+            if (got >= 0) __threadfence();
+            s_claim = got;
         }
-        const int k0 = chunk * g.chunk_steps;
-        const int k1 = min(k0 + g.chunk_steps, g.n_steps);
-        advance_system<T, kZeroEps>(g, b, k0, k1, s);
         __syncthreads();
-        if (threadIdx.x == 0) atomicExch(g.progress + b, chunk + 1);
+        return s_claim;
+    };
+    auto run_ticket = [&](int t) {
+        const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
+        const int k0 = chunk * g.chunk_steps, k1 = min(k0 + g.chunk_steps, g.n_steps);
+        load_state<T>(g, bl, s);
+        run_steps<T, kZeroEps>(g, bl, k0, k1, s);
+        store_state<T>(g, bl, s);
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(g.progress + bl, chunk + 1);
+    };
+
+    // Home boundaries (where a CTA may steal) are every kPeekSteps steps, staggered by CTA so that at every
+    // step some CTAs are at a boundary and a leftover chunk is picked up as soon as it becomes ready.
+    constexpr int kPeekSteps = 8;
+    const int phase = blockIdx.x % kPeekSteps;
+    for (int round = 0; round < home_rounds; ++round) {
+        const int b = blockIdx.x + round * grid;
+        load_state<T>(g, b, s);
+        int k0 = 0;
+        do {
+            int k1 = g.n_steps;
+            if (n_tickets && steals < steal_budget) {
+                const int d = ((k0 - phase) % kPeekSteps + kPeekSteps) % kPeekSteps;
+                k1 = min(k0 + (kPeekSteps - d), g.n_steps);
+            }
+            run_steps<T, kZeroEps>(g, b, k0, k1, s);
+            const bool last = k1 >= g.n_steps;
+            if (last) store_state<T>(g, b, s);
+            if (n_tickets && steals < steal_budget) {
+                const int t = claim(false);
+                if (t >= 0) {
+                    if (!last) store_state<T>(g, b, s);
+                    run_ticket(t);
+                    ++steals;
+                    if (!last) load_state<T>(g, b, s);
+                }
+            }
+            k0 = k1;
+        } while (k0 < g.n_steps);
+    }
+    // whatever leftover work is still unclaimed (short runs with a single chunk, or no home round at all)
+    while (n_tickets) {
+        const int t = claim(true);
+        if (t < 0) break;
+        run_ticket(t);
     }
 }
 
@@ -308,18 +393,29 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     NB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     NB_REQUIRE(per_sm >= 1, "ensemble kernel does not fit on an SM (N=%d threads=%d smem=%zu)", N, threads, smem);
     const int resident = per_sm * sms;
-    g.ticket = nullptr; g.progress = nullptr; g.chunk_steps = n_steps; g.n_chunks = 1;
-    int grid = B < resident ? B : resident;
-    if (B > resident && n_steps >= 8) {
-        // ticket mode: ~48 tickets per resident CTA (tail and hand-over waits of a percent or two),
-        // chunks of at least 4 steps (state reload amortised)
+    const int grid = B < resident ? B : resident;
+    // Leftover systems (B mod grid) advance in chunks of 20 steps, each chunk stolen by a home CTA.
+    g.ticket = nullptr; g.progress = nullptr; g.chunk_steps = n_steps > 0 ? n_steps : 1; g.n_chunks = 1;
+    g.home_rounds = B / grid;
+    if (B % grid != 0) {
         NB_REQUIRE(ws && ws_bytes >= nb_ensemble_workspace_bytes(B), "ensemble workspace too small: %zu < %zu",
                    ws_bytes, nb_ensemble_workspace_bytes(B));
-        const int want = ceil_div(48 * resident, B);
-        int steps = ceil_div(n_steps, want);
-        if (steps < 4) steps = 4;
-        g.chunk_steps = steps;
-        g.n_chunks = ceil_div(n_steps, steps);
+        if (B % grid <= grid / 8) {
+            // a few leftover systems: 20-step chunks stolen by the home CTAs
+            if (n_steps >= 40) {
+                g.chunk_steps = 20;
+                g.n_chunks = ceil_div(n_steps, 20);
+            }
+        } else {
+            // many: no home systems, every system advances by tickets (~48 per CTA, chunks of >= 8 steps)
+            g.home_rounds = 0;
+            int steps = ceil_div(n_steps, ceil_div(48 * grid, B));
+            if (steps < 8) steps = 8;
+            if (n_steps >= 16) {
+                g.chunk_steps = steps;
+                g.n_chunks = ceil_div(n_steps, steps);
+            }
+        }
         g.ticket = static_cast<int*>(ws);
         g.progress = g.ticket + 1;
         NB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(int) * ((size_t)B + 1), st));

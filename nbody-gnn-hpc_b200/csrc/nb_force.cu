@@ -62,8 +62,10 @@ __device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stre
     return stream[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
 }
 
+// __launch_bounds__(kBlock, 512 / kBlock): two 256-thread (or four 128-thread) CTAs per SM and up to 128
+// registers; without the second argument ptxas settles for 76 registers and a 3% slower schedule.
 template <int kP, int kBlock, bool kZeroEps>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 512 / kBlock)
 force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, float eps2,
                  float* __restrict__ partial) {
     __shared__ __align__(128) char ring[kStages * kTileBytes];

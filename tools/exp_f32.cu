@@ -8,6 +8,16 @@
 #include "../nbody-gnn-hpc_b200/csrc/nb_common.cuh"
 
 namespace nb { void set_error(const char*, ...) {} int cuda_fail(cudaError_t, const char*) { return 2; } }
+extern "C" { int nb_padded_bodies(int n) { return (n + 31) / 32 * 32; }
+int nb_segment_plan(int, int*, int*) { return 0; }
+size_t nb_workspace_bytes(int, int, int) { return 0; } }
+#define kStages kLibStages
+#define kTileBytes kLibTileBytes
+#define stream_tiles lib_stream_tiles
+#include "../nbody-gnn-hpc_b200/csrc/nb_force.cu"   // the library kernels, timed beside the variants below
+#undef kStages
+#undef kTileBytes
+#undef stream_tiles
 using namespace nb;
 
 constexpr int kStages = 4, kTileBytes = 4096;
@@ -112,6 +122,24 @@ void bench(const char* tag) {
     fflush(stdout);
 }
 
+template <int kP, int kBlock>
+void bench_lib(const char* tag) {
+    dim3 grid((N + kP * kBlock - 1) / (kP * kBlock), NSEG);
+    auto k = nb::force_f32_kernel<kP, kBlock, false>;
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        k<<<grid, kBlock>>>(d_stream, N, 0, N, SEGLEN, 1e-4f, d_partial);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (r > 1 && ms < best) best = ms;
+    }
+    printf("%-28s P=%d block=%d regs=%3d ctas=%5d  %.4f ms  %.1f Gint/s  (%.1f%% of 3722)\n", tag, kP, kBlock, fa.numRegs,
+           grid.x * grid.y, best, (double)N * (N - 1) / best / 1e6, (double)N * (N - 1) / best / 1e6 / 37.22);
+    fflush(stdout);
+}
+
 int main(int argc, char** argv) {
     N = argc > 1 ? atoi(argv[1]) : 65536;
     SEGLEN = argc > 2 ? atoi(argv[2]) : 1024;
@@ -122,6 +150,9 @@ int main(int argc, char** argv) {
     cudaMalloc(&d_stream, h.size() * 4); cudaMemcpy(d_stream, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
     cudaMalloc(&d_partial, (size_t)NSEG * 3 * N * 4);
     printf("N=%d seg_len=%d n_seg=%d\n", N, SEGLEN, NSEG);
+    bench_lib<4, 256>("LIBRARY kernel"); bench_lib<2, 128>("LIBRARY kernel");
+    bench<4, 256, 15, 2, 1>("u2"); bench<4, 256, 15, 4, 1>("u4");
+    if (argc > 3) return 0;
 #define PACKS(P, B, U, M) \
     bench<P, B, 15, U, M>("all packed"); bench<P, B, 0, U, M>("all scalar"); bench<P, B, 1, U, M>("SUB"); bench<P, B, 2, U, M>("R2"); \
     bench<P, B, 4, U, M>("MUL"); bench<P, B, 8, U, M>("ACC"); bench<P, B, 3, U, M>("SUB+R2"); bench<P, B, 5, U, M>("SUB+MUL"); \

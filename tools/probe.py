@@ -51,7 +51,7 @@ def main():
                               "ms_median": round(med, 4), "Ginter_per_s": round(inter / best / 1e6, 1),
                               "seg_plan": eng.segment_plan(n)}), flush=True)
     # ensemble, datagen configuration
-    for B in (300, 296, 1200):
+    for B in (296, 300, 1200, 300, 450):
         x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=42)
         x, v = eng.to_device(x0), eng.to_device(v0)
         a = torch.zeros_like(x)
