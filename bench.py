@@ -370,7 +370,7 @@ def bench_single(args, world, rank, local, sharded: bool):
     eps = 0.01 if n <= 16384 else 1e-3
     x, v, m = ics.plummer_ic(n, seed=7)
     sysm = ShardedSystem(x, v, m, dt=1e-3, softening=eps, dtype=dtype, device=local,
-                         world=world if sharded else 1, rank=rank if sharded else 0)
+                         world=world if sharded else 1, rank=rank if sharded else 0, exchange=args.exchange)
     launches0 = eng.launches
 
     def step():
@@ -419,7 +419,9 @@ def bench_single(args, world, rank, local, sharded: bool):
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"single system N={n} Plummer, {args.sim_steps} leapfrog steps per bench step",
                    "softening": eps, "l2": "compute-bound; working set " + f"{n * 16 / 1e6:.1f} MB is L2-resident by design",
-                   "parallelism": (f"i-slab over {world} ranks, one all-gather of positions per step" if sharded
+                   "parallelism": (f"i-slab over {world} ranks, positions exchanged every step by "
+                                   + ("peer stores fused into the drift kernel + arrival words (no collective call)"
+                                      if sysm.exchange == "peer" else "one NCCL all-gather") if sharded
                                    else f"{world} independent replica(s)")},
         "sim_steps_per_s": round(replicas * args.steps * args.sim_steps / secs, 2),
         "e2e": e2e, "gpu_launches": launches,
@@ -451,6 +453,8 @@ def main():
     ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
     ap.add_argument("--bodies", type=int, default=65536)
     ap.add_argument("--sim-steps", type=int, default=10, help="leapfrog steps per bench step (single/sharded)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="sharded workload: how ranks exchange positions")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -108,6 +108,27 @@ int nb_step_f32(const float* stream_cur, float* stream_next, float* vel, float* 
                 double* snap_pos, double* snap_vel, double* snap_acc,
                 void* workspace, size_t workspace_bytes, nb_stream_t s);
 
+/* nb_step_* fused with its collective, for one system sharded by i-slab over the GPUs of a box (no
+ * counterpart in the reference, which is single-host).  Same arithmetic as nb_step_*, but the drift stores the
+ * slab's new positions directly into the next-stream buffer of EVERY rank over NVLink (peer pointers from
+ * symmetric / IPC-mapped memory), and ordering between ranks is carried by arrival words instead of a collective:
+ *   next_peers[r]   rank r's next-stream buffer (device pointer valid on this GPU), r = 0..n_ranks-1, own included
+ *   flag_peers[r]   rank r's flag array: >= 64 uint32, zero before first use; word q = last sequence number rank q
+ *                   published to rank r, word 32 = scratch counter of rank r's own kernels
+ *   wait_seq        the force pass reads stream_cur only after every rank has published >= wait_seq here (0: no wait)
+ *   signal_seq      published to every rank once this rank's whole slab has been stored (> 0, increasing per step)
+ * i0 must be a multiple of NB_CHUNK_BODIES.  Host arrays of n_ranks pointers; n_ranks <= 16. */
+int nb_step_peer_f64(const double* stream_cur, void* const* next_peers, void* const* flag_peers, int n_ranks,
+                     int my_rank, unsigned wait_seq, unsigned signal_seq, double* vel, double* acc,
+                     int n, int i0, int n_i, double dt, double softening, int flags,
+                     double* snap_pos, double* snap_vel, double* snap_acc,
+                     void* workspace, size_t workspace_bytes, nb_stream_t s);
+int nb_step_peer_f32(const float* stream_cur, void* const* next_peers, void* const* flag_peers, int n_ranks,
+                     int my_rank, unsigned wait_seq, unsigned signal_seq, float* vel, float* acc,
+                     int n, int i0, int n_i, double dt, double softening, int flags,
+                     double* snap_pos, double* snap_vel, double* snap_acc,
+                     void* workspace, size_t workspace_bytes, nb_stream_t s);
+
 /* Replaces the loop of NBodySimulator.run, reference src/hpc/nbody.py:237-241, on one GPU:
  * enqueues nb_kick_drift + n_steps x nb_step on stream s.  stream_a holds x_0 on entry; the two
  * stream buffers alternate and *final_in_a reports which one holds x_{n_steps}.  vel/acc hold

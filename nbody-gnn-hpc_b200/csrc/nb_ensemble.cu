@@ -78,6 +78,8 @@ struct EnsembleArgs {
     int parts;        // j-parts
     int chunk_steps;  // steps per leftover ticket
     int n_chunks;
+    int* sm_slots;    // per-SM arrival counter (zero on entry) used to stagger co-resident CTAs, or null
+    unsigned stagger_ns;  // delay of every second CTA of an SM, about half a step
     int home_rounds;  // whole grid-rounds of systems that stay resident in their CTA (0: everything by ticket)
     int* ticket;      // ticket mode: global ticket counter, zero on entry
     int* progress;    // ticket mode: per-system count of finished chunks, zero on entry
@@ -190,7 +192,7 @@ __device__ __forceinline__ void run_steps(const EnsembleArgs& g, int b, int k_be
                 const V4 me0 = s.pos[i0];
                 const V4 me1 = s.pos[has1 ? i1 : i0];
                 T ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
-#pragma unroll 2
+#pragma unroll 4
                 for (int j = jb; j < je; ++j) {
                     const V4 pj = s.pos[j];
                     pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
@@ -245,6 +247,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ensemble_kernel(const
     s.part = s.acc + n3;
     s.stage = s.part + (size_t)g.parts * n3;
     __shared__ int s_claim;
+
+    // Two CTAs share an SM and would run in lock step: both in the force phase (FP64 pipe saturated), then both
+    // in the integrate phase (pipe idle).  Delaying every second arrival on an SM by about half a step makes
+    // one CTA's integrate phase overlap the other's force phase for the rest of the run.
+    if (g.sm_slots != nullptr && g.stagger_ns > 0) {
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int arrival = atomicAdd(g.sm_slots + smid, 1);
+            if (arrival & 1) {
+                const long long t0 = clock64();
+                const long long ticks = (long long)g.stagger_ns * 2;  // ~2 GHz SM clock
+                while (clock64() - t0 < ticks) __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
 
     // Home systems: CTA c owns systems c, c + grid, ... (whole rounds of the grid) and keeps each one in
     // shared memory from its first step to its last.  Leftover systems (B mod grid of them) are advanced
@@ -397,6 +416,14 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     // Leftover systems (B mod grid) advance in chunks of 20 steps, each chunk stolen by a home CTA.
     g.ticket = nullptr; g.progress = nullptr; g.chunk_steps = n_steps > 0 ? n_steps : 1; g.n_chunks = 1;
     g.home_rounds = B / grid;
+    g.sm_slots = nullptr; g.stagger_ns = 0;
+    if (per_sm >= 2 && ws && ws_bytes >= nb_ensemble_workspace_bytes(B)) {
+        // half of one shared step: N^2 interactions x 16 FP64 ops on a 64-lane pipe at ~1.9 GHz
+        const double step_ns = (double)N * N * 16.0 / (64.0 * 1.9);
+        g.stagger_ns = (unsigned)(step_ns > 4.0e6 ? 4.0e6 : step_ns);
+        g.sm_slots = static_cast<int*>(ws) + (size_t)B + 1;
+        NB_CUDA_OK(cudaMemsetAsync(g.sm_slots, 0, sizeof(int) * 1024, st));
+    }
     if (B % grid != 0) {
         NB_REQUIRE(ws && ws_bytes >= nb_ensemble_workspace_bytes(B), "ensemble workspace too small: %zu < %zu",
                    ws_bytes, nb_ensemble_workspace_bytes(B));
@@ -430,7 +457,8 @@ extern "C" {
 
 int nb_ensemble_max_bodies(void) { return nb::kEnsembleMaxBodies; }
 
-size_t nb_ensemble_workspace_bytes(int B) { return (sizeof(int) * ((size_t)(B > 0 ? B : 0) + 1) + 255) / 256 * 256; }
+// ticket counter + per-system progress words + per-SM arrival counters
+size_t nb_ensemble_workspace_bytes(int B) { return (sizeof(int) * ((size_t)(B > 0 ? B : 0) + 1 + 1024) + 255) / 256 * 256; }
 
 int nb_ensemble_f64(double* x, double* v, double* a, const void* masses, int masses_are_f32, int mass_stride, int B,
                     int N, double dt, double softening, int n_steps, int save_interval, int compute_a0,

@@ -15,6 +15,8 @@
 // float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
 // (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
 // float64 inner loop: pair_f64() in nb_common.cuh, 16 FP64-pipe operations + 1 MUFU.RSQ64H.
+#include <type_traits>
+
 #include "nb_common.cuh"
 
 namespace nb {
@@ -56,6 +58,49 @@ __device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int t
 }
 
 // ------------------------------------------------------------------------------------------------
+// cross-GPU ordering for the sharded mode (nb_step_peer_*): arrival words in peer-visible memory
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+constexpr int kCounterSlot = 32;  // word of the local flag array used as the finish kernel's block counter
+
+struct PeerWait {          // force pass: do not read the stream before every rank has published wait_seq
+    const uint32_t* flags;  // local array, one word per rank (null: no wait)
+    int n_ranks;
+    uint32_t seq;
+};
+struct PeerTargets {       // finish pass: where the new slab goes and whom to tell
+    void* next[kMaxPeers];       // every rank's next-stream buffer (own included)
+    uint32_t* flags[kMaxPeers];  // every rank's flag array
+    int n_ranks, my_rank;
+    uint32_t seq;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Called by every thread at kernel entry; thread 0 spins (bounded) until all ranks have arrived.
+__device__ __forceinline__ void peer_wait(const PeerWait& w) {
+    if (w.flags == nullptr) return;
+    if (threadIdx.x < w.n_ranks) {  // one polling thread per rank: the loads overlap
+        long long spins = 0;
+        // sequence numbers wrap: compare as signed distance
+        while ((int32_t)(ld_acquire_sys(w.flags + threadIdx.x) - w.seq) < 0) {
+            __nanosleep(100);
+            if (++spins > (1LL << 26)) break;  // ~10 s: a peer died; do not hang the GPU
+        }
+    }
+    __syncthreads();
+    // the stream is read next through the async (TMA) proxy, issued by thread 0
+    if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // float32 force kernel
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stream, int body, int c) {
@@ -67,9 +112,10 @@ __device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stre
 template <int kP, int kBlock, bool kZeroEps>
 __global__ void __launch_bounds__(kBlock, 512 / kBlock)
 force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, float eps2,
-                 float* __restrict__ partial) {
+                 float* __restrict__ partial, const PeerWait wait) {
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
+    peer_wait(wait);
 
     const int seg = blockIdx.y;
     const int j0 = seg * seg_len;
@@ -141,9 +187,10 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
 template <int kP, int kBlock, bool kZeroEps>
 __global__ void __launch_bounds__(kBlock)
 force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, double eps2,
-                 double* __restrict__ partial) {
+                 double* __restrict__ partial, const PeerWait wait) {
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
+    peer_wait(wait);
 
     const int seg = blockIdx.y;
     const int j0 = seg * seg_len;
@@ -248,6 +295,78 @@ finish_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, const T
     }
 }
 
+// Bodies per 32-byte stream record.
+template <typename T> struct Record;
+template <> struct Record<double> { static constexpr int kBodies = 1; };
+template <> struct Record<float> { static constexpr int kBodies = 2; };
+
+// K2 fused with its collective: the same reduction + leapfrog as finish_kernel<T, true>, but a thread owns one
+// whole 32-byte stream record (one body in float64, a pair in float32) and stores the drifted record straight
+// into the next-stream buffer of EVERY rank (two 16-byte stores per peer over NVLink, consecutive threads ->
+// consecutive records).  When the last block of the grid is done, one thread publishes this rank's arrival word
+// on every rank; the peers' next force pass waits on those words (peer_wait) instead of on an NCCL all-gather.
+template <typename T>
+__global__ void __launch_bounds__(256)
+finish_peer_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, const T* __restrict__ stream_cur,
+                   T* __restrict__ vel, T* __restrict__ acc, T dt, T half_dt, int flags, double* __restrict__ snap_pos,
+                   double* __restrict__ snap_vel, double* __restrict__ snap_acc, const PeerTargets peers) {
+    constexpr int kB = Record<T>::kBodies;
+    using V = typename std::conditional<sizeof(T) == 8, double2, float4>::type;  // 16 bytes
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;  // record index within the slab (i0 is a multiple of 32)
+    const int n_units = (n_i + kB - 1) / kB;
+    if (u < n_units) {
+        const size_t rec = (size_t)(i0 / kB + u) * 2;  // in 16-byte units
+        V lo = reinterpret_cast<const V*>(stream_cur)[rec];
+        V hi = reinterpret_cast<const V*>(stream_cur)[rec + 1];
+        T* w = reinterpret_cast<T*>(&lo);   // float64: x y | z gm      float32: x0 x1 y0 y1 | z0 z1 gm0 gm1
+        T* wh = reinterpret_cast<T*>(&hi);
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+            const int li = u * kB + b;
+            if (li >= n_i) break;
+            const int gi = i0 + li;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T a = T(0);
+                for (int sg = 0; sg < n_seg; ++sg) a += partial[((size_t)sg * 3 + c) * n_i + li];
+                T* slot = (sizeof(T) == 8) ? (c < 2 ? w + c : wh) : (c < 2 ? w + 2 * c + b : wh + b);
+                T x = *slot;
+                T v = vel[(size_t)li * 3 + c];
+                v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
+                if (flags & NB_STEP_SNAPSHOT) {
+                    if (snap_pos) snap_pos[(size_t)gi * 3 + c] = (double)x;
+                    if (snap_vel) snap_vel[(size_t)gi * 3 + c] = (double)v;
+                    if (snap_acc) snap_acc[(size_t)gi * 3 + c] = (double)a;
+                }
+                if (flags & NB_STEP_CONTINUE) {
+                    v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
+                    x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
+                    *slot = x;
+                }
+                vel[(size_t)li * 3 + c] = v;
+                acc[(size_t)li * 3 + c] = a;
+            }
+        }
+        if (flags & NB_STEP_CONTINUE) {
+            for (int p = 0; p < peers.n_ranks; ++p) {
+                V* dst = reinterpret_cast<V*>(peers.next[p]) + rec;
+                dst[0] = lo;
+                dst[1] = hi;
+            }
+        }
+    }
+    __threadfence_system();  // this thread's peer stores are ordered before the arrival word
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(peers.flags[peers.my_rank] + kCounterSlot);
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {  // last block of this rank
+            *counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < peers.n_ranks; ++p) st_release_sys(peers.flags[p] + peers.my_rank, peers.seq);
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 kick_drift_kernel(const T* __restrict__ stream_cur, T* __restrict__ stream_next, T* __restrict__ vel,
@@ -329,16 +448,18 @@ struct Tile<double> {
 };
 
 template <int kP, int kBlock, bool kZeroEps>
-static void launch_force(const float* stream, const Slab& sl, float eps2, float* partial, cudaStream_t st) {
+static void launch_force(const float* stream, const Slab& sl, float eps2, float* partial, const PeerWait& w,
+                         cudaStream_t st) {
     dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
     force_f32_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
-                                                                     partial);
+                                                                     partial, w);
 }
 template <int kP, int kBlock, bool kZeroEps>
-static void launch_force(const double* stream, const Slab& sl, double eps2, double* partial, cudaStream_t st) {
+static void launch_force(const double* stream, const Slab& sl, double eps2, double* partial, const PeerWait& w,
+                         cudaStream_t st) {
     dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
     force_f64_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
-                                                                     partial);
+                                                                     partial, w);
 }
 
 static int g_sm_count = 0;
@@ -353,7 +474,8 @@ static int sm_count() {
 }
 
 template <typename T>
-static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st) {
+static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st,
+                      const PeerWait& w = PeerWait{nullptr, 0, 0}) {
     const T eps2 = (T)(softening * softening);
     const bool zero = !(eps2 > T(0));
     using TL = Tile<T>;
@@ -361,11 +483,11 @@ static int force_pass(const T* stream, const Slab& sl, double softening, T* part
     const long ctas_big = (long)ceil_div(sl.n_i, TL::kPBig * TL::kBlockBig) * sl.n_seg;
     const bool big = ctas_big >= 4L * sm_count();
     if (big) {
-        if (zero) launch_force<TL::kPBig, TL::kBlockBig, true>(stream, sl, eps2, partial, st);
-        else launch_force<TL::kPBig, TL::kBlockBig, false>(stream, sl, eps2, partial, st);
+        if (zero) launch_force<TL::kPBig, TL::kBlockBig, true>(stream, sl, eps2, partial, w, st);
+        else launch_force<TL::kPBig, TL::kBlockBig, false>(stream, sl, eps2, partial, w, st);
     } else {
-        if (zero) launch_force<TL::kPSmall, TL::kBlockSmall, true>(stream, sl, eps2, partial, st);
-        else launch_force<TL::kPSmall, TL::kBlockSmall, false>(stream, sl, eps2, partial, st);
+        if (zero) launch_force<TL::kPSmall, TL::kBlockSmall, true>(stream, sl, eps2, partial, w, st);
+        else launch_force<TL::kPSmall, TL::kBlockSmall, false>(stream, sl, eps2, partial, w, st);
     }
     return check_launch("force kernel");
 }
@@ -400,6 +522,36 @@ static int step_impl(const T* cur, T* next, T* vel, T* acc, int n, int i0, int n
     finish_kernel<T, true><<<ceil_div(n_i, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, next, vel, acc, (T)dt,
                                                                 (T)half_dt, flags, sp, sv, sa);
     return check_launch("finish kernel");
+}
+
+template <typename T>
+static int step_peer_impl(const T* cur, void* const* next_peers, void* const* flag_peers, int n_ranks, int my_rank,
+                          unsigned wait_seq, unsigned signal_seq, T* vel, T* acc, int n, int i0, int n_i, double dt,
+                          double softening, int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+    Slab sl;
+    if (int rc = make_slab(n, i0, n_i, &sl)) return rc;
+    NB_REQUIRE(cur && vel && acc && ws && next_peers && flag_peers, "null pointer argument");
+    NB_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxPeers && my_rank >= 0 && my_rank < n_ranks,
+               "need 1 <= n_ranks <= %d and 0 <= my_rank < n_ranks", kMaxPeers);
+    NB_REQUIRE(i0 % kChunkBodies == 0, "slab start must be a multiple of %d bodies", kChunkBodies);
+    NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
+               nb_workspace_bytes(n, n_i, sizeof(T) == 8));
+    PeerTargets tg;
+    for (int p = 0; p < n_ranks; ++p) {
+        NB_REQUIRE(next_peers[p] && flag_peers[p], "null peer pointer for rank %d", p);
+        tg.next[p] = next_peers[p];
+        tg.flags[p] = static_cast<uint32_t*>(flag_peers[p]);
+    }
+    tg.n_ranks = n_ranks; tg.my_rank = my_rank; tg.seq = signal_seq;
+    PeerWait w{wait_seq ? tg.flags[my_rank] : nullptr, n_ranks, wait_seq};
+    T* partial = static_cast<T*>(ws);
+    if (int rc = force_pass<T>(cur, sl, softening, partial, st, w)) return rc;
+    const double half_dt = 0.5 * dt;
+    const int units = ceil_div(n_i, Record<T>::kBodies);
+    finish_peer_kernel<T><<<ceil_div(units, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, vel, acc, (T)dt,
+                                                                  (T)half_dt, flags, sp, sv, sa, tg);
+    return check_launch("finish_peer kernel");
 }
 
 template <typename T>
@@ -521,6 +673,21 @@ int nb_step_f32(const float* cur, float* next, float* vel, float* acc, int n, in
                 nb_stream_t s) {
     return nb::step_impl<float>(cur, next, vel, acc, n, i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes,
                                 (cudaStream_t)s);
+}
+
+int nb_step_peer_f64(const double* cur, void* const* next_peers, void* const* flag_peers, int n_ranks, int my_rank,
+                     unsigned wait_seq, unsigned signal_seq, double* vel, double* acc, int n, int i0, int n_i, double dt,
+                     double softening, int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+                     nb_stream_t s) {
+    return nb::step_peer_impl<double>(cur, next_peers, flag_peers, n_ranks, my_rank, wait_seq, signal_seq, vel, acc, n,
+                                      i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes, (cudaStream_t)s);
+}
+int nb_step_peer_f32(const float* cur, void* const* next_peers, void* const* flag_peers, int n_ranks, int my_rank,
+                     unsigned wait_seq, unsigned signal_seq, float* vel, float* acc, int n, int i0, int n_i, double dt,
+                     double softening, int flags, double* sp, double* sv, double* sa, void* ws, size_t ws_bytes,
+                     nb_stream_t s) {
+    return nb::step_peer_impl<float>(cur, next_peers, flag_peers, n_ranks, my_rank, wait_seq, signal_seq, vel, acc, n,
+                                     i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes, (cudaStream_t)s);
 }
 
 int nb_run_f64(double* stream_a, double* stream_b, double* vel, double* acc, int n, double dt, double softening,

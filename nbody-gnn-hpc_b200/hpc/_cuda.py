@@ -52,6 +52,10 @@ _SIGNATURES = {
     "nb_kick_drift_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _vp]),
     "nb_step_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nb_step_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nb_step_peer_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci,
+                               _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nb_step_peer_f32": (_ci, [_vp, _vp, _vp, _ci, _ci, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci,
+                               _vp, _vp, _vp, _vp, _sz, _vp]),
     "nb_run_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_run_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_ensemble_max_bodies": (_ci, []),
@@ -255,6 +259,22 @@ class Engine:
             self._p(cur), self._p(nxt), self._p(vel), self._p(acc), n, i0, n_i, float(dt), float(softening),
             int(flags), self._p(snap_pos), self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1],
             self._stream()))
+        self.launches += 2
+
+    def step_peer_slab(self, cur, next_ptrs, flag_ptrs, my_rank: int, wait_seq: int, signal_seq: int, vel, acc,
+                       n: int, i0: int, n_i: int, dt: float, softening: float, flags: int, snap_pos, snap_vel,
+                       snap_acc, ws):
+        """K2 fused with its collective: the slab's new positions are stored into every rank's next stream
+        (next_ptrs: device pointers as ints, own rank included) and ordering is by arrival words (flag_ptrs)."""
+        torch = _torch()
+        sfx = "f64" if cur.dtype == torch.float64 else "f32"
+        P = len(next_ptrs)
+        nxt = (ctypes.c_void_p * P)(*[int(q) for q in next_ptrs])
+        flg = (ctypes.c_void_p * P)(*[int(q) for q in flag_ptrs])
+        self._check(getattr(self.lib, f"nb_step_peer_{sfx}")(
+            self._p(cur), nxt, flg, P, int(my_rank), int(wait_seq) & 0xFFFFFFFF, int(signal_seq) & 0xFFFFFFFF,
+            self._p(vel), self._p(acc), n, i0, n_i, float(dt), float(softening), int(flags), self._p(snap_pos),
+            self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1], self._stream()))
         self.launches += 2
 
     # ---- host-level operations (ndarrays in, ndarrays out; the reference's call shapes) ----------

@@ -43,7 +43,7 @@ class ShardedSystem:
     """Device-resident state of one system, advanced slab-wise.  world == 1 is the plain one-GPU case."""
 
     def __init__(self, positions, velocities, masses, dt: float, softening: float, dtype=np.float64, device=None,
-                 world: int = 1, rank: int = 0, group=None, engine=None, accelerations=None):
+                 world: int = 1, rank: int = 0, group=None, engine=None, accelerations=None, exchange: str = "auto"):
         import torch
         self.torch = torch
         self.eng = engine if engine is not None else _cuda.get_engine(device)
@@ -65,9 +65,33 @@ class ShardedSystem:
         pos_d = eng.to_device(pos)
         m_d, f32 = eng._masses_dev(self.masses_host)
         self._m_d, self._m_f32 = m_d, f32
-        self.cur = torch.zeros(total * 4, dtype=tdt, device=eng.device)
+        # exchange: "nccl" = one in-place all-gather per step; "peer" = the drift kernel stores its slab into
+        # every rank's stream over NVLink and ranks order themselves with arrival words (no collective call);
+        # "auto" = peer when torch symmetric memory can map the buffers, else nccl.
+        self.exchange = "nccl"
+        self._peer = None
+        every_rank_has_bodies = all(hi > lo for lo, hi in bounds)
+        if self.world > 1 and exchange in ("auto", "peer") and engine is None and every_rank_has_bodies:
+            try:
+                self._peer = self._setup_peer(total * 4, tdt)
+                self.exchange = "peer"
+            except Exception as e:  # symmetric memory unavailable on this build / topology
+                if exchange == "peer":
+                    raise
+                self._peer_error = repr(e)
+        if self._peer is not None:
+            self.cur, self.nxt = self._peer["bufs"]
+            self.cur.zero_()
+        else:
+            self.cur = torch.zeros(total * 4, dtype=tdt, device=eng.device)
         eng.pack(pos_d, m_d, f32, self.n, self.dtype, out=self.cur)
-        self.nxt = self.cur.clone()
+        if self._peer is not None:
+            self.nxt.copy_(self.cur)
+            self._seq = 0
+            torch.cuda.synchronize(eng.device)
+            self.dist.barrier(group=self.group)
+        else:
+            self.nxt = self.cur.clone()
         sl = slice(self.i0, self.i0 + self.n_i)
         vel = np.ascontiguousarray(velocities, dtype=np.float64)[sl]
         self.vel = eng.to_device(np.ascontiguousarray(vel), tdt) if self.n_i else torch.zeros((0, 3), dtype=tdt, device=eng.device)
@@ -79,6 +103,22 @@ class ShardedSystem:
             acc = np.ascontiguousarray(accelerations, dtype=np.float64)[sl]
             self.acc = eng.to_device(np.ascontiguousarray(acc), tdt) if self.n_i else torch.zeros((0, 3), dtype=tdt, device=eng.device)
         self.steps_done = 0
+
+    def _setup_peer(self, n_elems: int, tdt):
+        """Both stream buffers in symmetric memory: peer pointers for the stores, signal pads for the arrival words."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else self.dist.group.WORLD
+        bufs, handles = [], []
+        for _ in range(2):
+            t = symm.empty(n_elems, dtype=tdt, device=self.eng.device)
+            handles.append(symm.rendezvous(t, group))
+            bufs.append(t)
+        ptrs = [[int(p) for p in h.buffer_ptrs] for h in handles]
+        flags = [int(p) for p in handles[0].signal_pad_ptrs]
+        if handles[0].signal_pad_size < 64 * 4:
+            raise RuntimeError("signal pad too small")
+        return {"bufs": bufs, "handles": handles, "ptrs": {bufs[0].data_ptr(): ptrs[0], bufs[1].data_ptr(): ptrs[1]},
+                "flags": flags}
 
     # -- communication --------------------------------------------------------------------------
     def _exchange(self, stream):
@@ -102,16 +142,28 @@ class ShardedSystem:
             save = snap_pos is not None and (k % save_interval) == 0
             if save:
                 flags |= _cuda.NB_STEP_SNAPSHOT
-            if self.n_i:
-                eng.step_slab(self.cur, self.nxt, self.vel, self.acc, self.n, self.i0, self.n_i, self.dt,
-                              self.softening, flags,
-                              snap_pos[snap] if save else None, snap_vel[snap] if save else None,
-                              snap_acc[snap] if save else None, self.ws)
+            sp = snap_pos[snap] if save else None
+            sv = snap_vel[snap] if save else None
+            sa = snap_acc[snap] if save else None
+            if self._peer is not None:
+                # fused: force + leapfrog + store of the slab into every rank's next stream + arrival word.
+                # The first step of an advance() reads a stream that NCCL completed (no wait needed).
+                self._seq += 1
+                wait = self._seq - 1 if k > 1 else 0
+                eng.step_peer_slab(self.cur, self._peer["ptrs"][self.nxt.data_ptr()], self._peer["flags"], self.rank,
+                                   wait, self._seq, self.vel, self.acc, self.n, self.i0, max(self.n_i, 0), self.dt,
+                                   self.softening, flags, sp, sv, sa, self.ws)
+                if k < n_steps:
+                    self.cur, self.nxt = self.nxt, self.cur
+            else:
+                if self.n_i:
+                    eng.step_slab(self.cur, self.nxt, self.vel, self.acc, self.n, self.i0, self.n_i, self.dt,
+                                  self.softening, flags, sp, sv, sa, self.ws)
+                if k < n_steps:
+                    self._exchange(self.nxt)
+                    self.cur, self.nxt = self.nxt, self.cur
             if save:
                 snap += 1
-            if k < n_steps:
-                self._exchange(self.nxt)
-                self.cur, self.nxt = self.nxt, self.cur
         self.steps_done += n_steps
 
     # -- results --------------------------------------------------------------------------------

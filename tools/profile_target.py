@@ -24,8 +24,8 @@ if "f32" in which or "f64" in which:
             for _ in range(2):
                 eng.accel_slab(stream, n, 0, n, 0.01, ws)
             torch.cuda.synchronize()
-if "ens" in which:
-    B, steps = 296, 50
+if "ens" in which or "ens400" in which:
+    B, steps = (300, 400) if "ens400" in which else (296, 50)
     x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=42)
     x, v = eng.to_device(x0), eng.to_device(v0)
     a = torch.zeros_like(x)
