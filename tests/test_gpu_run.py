@@ -276,3 +276,18 @@ def test_sharded_system_single_rank_matches_simulator(oracle_mod):
     assert np.abs(sysm.velocities() - chk["final_velocities"]).max() < POS_TOL
     e = oracle_mod.total_energy(chk["final_positions"], chk["final_velocities"], m, 0.01, parallel=True)
     assert np.allclose(sysm.energy(), e, rtol=1e-10)
+
+
+def test_config3_n16384_both_precisions_vs_oracle(oracle_mod):
+    """BASELINE config 3 (single system N = 16,384 Plummer), shortened to 40 steps so the CPU oracle stays at
+    a few seconds: float64 within 1e-8 on positions, float32 within 1e-5 relative (max-norm)."""
+    from hpc import ics
+    x, v, m = ics.plummer_ic(16384, seed=7)
+    a0 = oracle_mod.accel_direct(x, m, 0.01)
+    chk = oracle_mod.run(x, v, a0, m, 1e-3, 0.01, 40, 40)
+    for dtype, tol in (("float64", POS_TOL), ("float32", 1e-5 * np.abs(chk["final_positions"]).max())):
+        sim = _sim_from(x, v, m, 1e-3, 0.01, dtype=dtype)
+        states = sim.run(40, save_interval=40, verbose=False)
+        assert len(states) == 2
+        assert np.abs(states[-1]["positions"] - chk["final_positions"]).max() < tol
+        assert np.abs(states[-1]["velocities"] - chk["final_velocities"]).max() < max(tol, 1e-5 * np.abs(chk["final_velocities"]).max() if dtype == "float32" else tol)
