@@ -2,6 +2,7 @@
 container only: /root/reference is not on the GPU box).  CUDA is replaced by the oracle-backed stand-in and
 h5py by tests/fake_h5py.py, so this checks the drop-in boundary -- imports, constructor/attribute protocol,
 state dicts, checkpoint files, dataset builder -- not the arithmetic."""
+import os
 import runpy
 import sys
 from pathlib import Path
@@ -24,6 +25,14 @@ def test_generate_data_script_runs_unchanged(monkeypatch, tmp_path, oracle_mod, 
     from hpc import ics, nbody
     assert "nbody-gnn-hpc_b200" in hpc.__file__
     nbody._set_backend_for_tests(FakeEngine())
+    # the script prepends <reference>/src to sys.path and pins thread-count env vars: undo both afterwards
+    monkeypatch.setattr(sys, "path", list(sys.path))
+    for var in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        if var in os.environ:
+            monkeypatch.setenv(var, os.environ[var])
+        else:
+            monkeypatch.setenv(var, "1")
+            monkeypatch.delenv(var)
     out = tmp_path / "data"
     monkeypatch.setattr(sys, "argv", ["generate_data.py", "--particles", "24", "--simulations", "5", "--steps", "12",
                                       "--workers", "1", "--output-dir", str(out), "--sequence-length", "5",

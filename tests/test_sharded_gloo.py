@@ -22,8 +22,9 @@ def _free_port():
 
 def _worker(rank, world, port, n, n_steps, save_interval, q):
     for p in (str(ROOT), str(ROOT / "nbody-gnn-hpc_b200"), str(ROOT / "tests")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
     from fake_engine import FakeEngine
     from hpc import ics
     from hpc.sharded import ShardedSystem
