@@ -41,6 +41,7 @@ extern "C" {
 /* nb_step_* flags */
 #define NB_STEP_CONTINUE 1    /* after the closing kick, also do the next step's opening kick + drift */
 #define NB_STEP_SNAPSHOT 2    /* write (x, v, a) of the synchronised state to the snapshot rows */
+#define NB_STEP_PEER_SYNC 4   /* nb_step_peer_*: do not finish before every rank has published signal_seq here */
 
 typedef void* nb_stream_t;
 
@@ -117,6 +118,8 @@ int nb_step_f32(const float* stream_cur, float* stream_next, float* vel, float* 
  *                   published to rank r, word 32 = scratch counter of rank r's own kernels
  *   wait_seq        the force pass reads stream_cur only after every rank has published >= wait_seq here (0: no wait)
  *   signal_seq      published to every rank once this rank's whole slab has been stored (> 0, increasing per step)
+ *   NB_STEP_PEER_SYNC in flags: the call additionally waits (on the device, in its last thread block) until every
+ *                   rank has published signal_seq here, so the next launch needs no wait_seq
  * i0 must be a multiple of NB_CHUNK_BODIES.  Host arrays of n_ranks pointers; n_ranks <= 16. */
 int nb_step_peer_f64(const double* stream_cur, void* const* next_peers, void* const* flag_peers, int n_ranks,
                      int my_rank, unsigned wait_seq, unsigned signal_seq, double* vel, double* acc,

@@ -357,12 +357,27 @@ finish_peer_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, co
     }
     __threadfence_system();  // this thread's peer stores are ordered before the arrival word
     __syncthreads();
+    __shared__ int s_last;
     if (threadIdx.x == 0) {
         unsigned* counter = reinterpret_cast<unsigned*>(peers.flags[peers.my_rank] + kCounterSlot);
-        if (atomicAdd(counter, 1u) == gridDim.x - 1) {  // last block of this rank
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;  // last block of this rank
+        if (s_last) {
             *counter = 0;
             __threadfence_system();
-            for (int p = 0; p < peers.n_ranks; ++p) st_release_sys(peers.flags[p] + peers.my_rank, peers.seq);
+        }
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < peers.n_ranks) {
+        // one thread per peer: publish this rank's arrival there, then (NB_STEP_PEER_SYNC) wait for that peer's
+        // arrival here, so the kernel boundary alone orders the next force pass after every rank's stores
+        st_release_sys(peers.flags[threadIdx.x] + peers.my_rank, peers.seq);
+        if (flags & NB_STEP_PEER_SYNC) {
+            const uint32_t* mine = peers.flags[peers.my_rank] + threadIdx.x;
+            long long spins = 0;
+            while ((int32_t)(ld_acquire_sys(mine) - peers.seq) < 0) {
+                __nanosleep(50);
+                if (++spins > (1LL << 27)) break;  // a peer died; do not hang the GPU
+            }
         }
     }
 }

@@ -21,6 +21,7 @@ LIB_PATH = _PKG / "lib" / "libnbody_b200.so"
 
 NB_STEP_CONTINUE = 1
 NB_STEP_SNAPSHOT = 2
+NB_STEP_PEER_SYNC = 4
 
 # N at or below which a single system runs through the one-launch ensemble kernel (K3, B = 1)
 # instead of one force launch per step (K1/K2).

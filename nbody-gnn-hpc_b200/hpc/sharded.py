@@ -148,11 +148,12 @@ class ShardedSystem:
             if self._peer is not None:
                 # fused: force + leapfrog + store of the slab into every rank's next stream + arrival word.
                 # The first step of an advance() reads a stream that NCCL completed (no wait needed).
+                # The kernel's last block waits for every rank's arrival word (NB_STEP_PEER_SYNC), so the next
+                # force pass needs no wait of its own.
                 self._seq += 1
-                wait = self._seq - 1 if k > 1 else 0
                 eng.step_peer_slab(self.cur, self._peer["ptrs"][self.nxt.data_ptr()], self._peer["flags"], self.rank,
-                                   wait, self._seq, self.vel, self.acc, self.n, self.i0, max(self.n_i, 0), self.dt,
-                                   self.softening, flags, sp, sv, sa, self.ws)
+                                   0, self._seq, self.vel, self.acc, self.n, self.i0, self.n_i, self.dt,
+                                   self.softening, flags | _cuda.NB_STEP_PEER_SYNC, sp, sv, sa, self.ws)
                 if k < n_steps:
                     self.cur, self.nxt = self.nxt, self.cur
             else:
