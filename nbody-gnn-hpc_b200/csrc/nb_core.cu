@@ -57,13 +57,13 @@ int nb_padded_bodies(int n) {
 // The j axis is cut into n_seg segments of seg_len bodies (the last may be shorter).  The plan is
 // a function of n alone, so a body's acceleration is the same bits whether it is evaluated by a
 // one-GPU launch or inside any rank's i-slab.  Policy: segments of n/16 bodies clamped to
-// [1024, 4096] (measured flat in that range at N = 65,536; longer segments mean fewer partials for
+// [256, 4096] (measured flat from 1024 up at N = 65,536; longer segments mean fewer partials for
 // the finish pass), at most 64 segments -- enough CTAs (i-tiles x segments) to fill 148 SMs several
 // times over from n ~ 16k up, even when eight ranks each take an eighth of the i-tiles.
 int nb_segment_plan(int n, int* seg_len, int* n_seg) {
     const int n_pad = nb_padded_bodies(n);
     int len = nb::round_up(nb::ceil_div(n_pad, 16), nb::kChunkBodies);
-    if (len < 1024) len = 1024;
+    if (len < 256) len = 256;  // mid-size systems (1k..16k bodies): short serial chains, more CTAs
     if (len > 4096) len = 4096;
     if (nb::ceil_div(n_pad, len) > 64) len = nb::round_up(nb::ceil_div(n_pad, 64), nb::kChunkBodies);
     if (len > n_pad) len = n_pad;

@@ -19,12 +19,14 @@
 // For N = 200 this is 100 rows x 5 parts = 500 threads -> 16 warps, four per scheduler, two CTAs
 // per SM: the four FP64 pipes of an SM carry equal load (13-warp CTAs lost 20% to that skew).
 //
-// Scheduling.  The grid is persistent: at most (resident CTAs per SM) x (SM count) CTAs.  If the
-// ensemble fits (B <= grid) every CTA runs its system start to finish.  Otherwise the run is cut
-// into short step chunks and CTAs draw (chunk, system) tickets from a global counter, chunk-major;
-// a system's state is handed from chunk to chunk through the in/out state arrays and a per-system
-// progress word.  A ticket's predecessor always has a lower ticket number, hence a CTA that is
-// already running, so the waits cannot deadlock.  This removes the 300-systems-on-148-SMs tail.
+// Scheduling.  The grid is persistent: at most (resident CTAs per SM) x (SM count) CTAs.  Whole
+// grid-rounds of systems are "home" systems: a CTA keeps its system in shared memory from the first
+// step to the last.  The B mod grid leftover systems (4 of 300 on 148 SMs) advance in step chunks
+// that home CTAs steal at their own (staggered) step boundaries -- (chunk, system) tickets from a
+// global counter, chunk-major; a system's state is handed from chunk to chunk through the in/out
+// state arrays and a per-system progress word.  With many leftovers every system advances by
+// tickets.  A ticket's predecessor always has a lower ticket number, hence a CTA that is already
+// running, so the waits cannot deadlock.  This removes the 300-systems-on-148-SMs tail.
 #include "nb_common.cuh"
 
 namespace nb {

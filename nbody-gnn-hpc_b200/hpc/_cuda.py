@@ -25,7 +25,7 @@ NB_STEP_PEER_SYNC = 4
 
 # N at or below which a single system runs through the one-launch ensemble kernel (K3, B = 1)
 # instead of one force launch per step (K1/K2).
-SMALL_SYSTEM_MAX_BODIES = 512
+SMALL_SYSTEM_MAX_BODIES = 320    # measured crossover on B200: K3 (B=1) 12-26 us/step at N=256-384, K2 floor 13-21 us
 
 
 class EngineUnavailable(RuntimeError):
@@ -376,7 +376,14 @@ class Engine:
         else:
             raise ValueError(f"masses must be (N,) or (B,N); got {m.shape}")
         if N > int(self.lib.nb_ensemble_max_bodies()):
-            raise ValueError(f"ensemble kernel holds at most {self.lib.nb_ensemble_max_bodies()} bodies per system")
+            # systems too large for one CTA's shared memory: each fills the GPU on its own (K1/K2), one after the other
+            outs = []
+            for b in range(B):
+                mb = m if mass_stride == 0 else m[b]
+                ab = self.accelerations(x0[b], mb, softening, dtype) if a0 is None else np.asarray(a0)[b]
+                outs.append(self.run(x0[b], v0[b], ab, mb, dt, softening, n_steps, save_interval, dtype=dtype,
+                                     snapshots=snapshots))
+            return {k: np.stack([o[k] for o in outs]) for k in outs[0]}
         n_snap = 1 + n_steps // save_interval
         with torch.cuda.device(self.device):
             x = self.to_device(x0)
