@@ -357,6 +357,24 @@ def single_system_extras(eng) -> dict:
         out[f"single_system_N{n}_{tag}"] = {"Ginteractions_per_s": round(gi, 1), "ms_per_force_eval": round(ms, 4),
                                             "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / peak_tf, 4),
                                             "peak_tflops": round(peak_tf, 2)}
+    del stream, ws
+    # the metric's other size, N = 1,048,576 (config 5), float32: two full leapfrog steps on this one GPU
+    from hpc.sharded import ShardedSystem
+    n = 1 << 20
+    x, v, m = ics.plummer_ic(n, seed=7)
+    sysm = ShardedSystem(x, v, m, dt=1e-3, softening=1e-3, dtype=np.float32, device=eng.device)
+    sysm.advance(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sysm.advance(2)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    gi = n * (n - 1.0) / ms / 1e6
+    peak_tf = eng.sm_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    out[f"single_system_N{n}_f32_leapfrog"] = {"Ginteractions_per_s": round(gi, 1), "sim_steps_per_s": round(1e3 / ms, 3),
+                                               "ms_per_step": round(ms, 2),
+                                               "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / peak_tf, 4)}
     return out
 
 

@@ -291,3 +291,44 @@ def test_config3_n16384_both_precisions_vs_oracle(oracle_mod):
         assert len(states) == 2
         assert np.abs(states[-1]["positions"] - chk["final_positions"]).max() < tol
         assert np.abs(states[-1]["velocities"] - chk["final_velocities"]).max() < max(tol, 1e-5 * np.abs(chk["final_velocities"]).max() if dtype == "float32" else tol)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 257, 600, 1024, 1100])
+def test_ensemble_body_counts(oracle_mod, n):
+    """K3 thread layouts at the edges: one body, odd counts (dummy second body), one part only, the
+    one-CTA-per-SM variant (N > ~500), the shared-memory limit (1024) and the per-system fallback above it."""
+    from hpc.ensemble import simulate_ensemble
+    rng = np.random.RandomState(n)
+    B = 3
+    x0 = rng.rand(B, n, 3) * 4 - 2
+    v0 = rng.rand(B, n, 3) - 0.5
+    m = rng.uniform(1e9, 1e10, n)
+    out = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, n_steps=6, save_interval=2)
+    assert out["positions"].shape == (B, 4, n, 3)
+    for b in range(B):
+        chk = oracle_mod.run(x0[b], v0[b], oracle_mod.accel_direct(x0[b], m, 0.05), m, 1e-3, 0.05, 6, 2)
+        assert np.abs(out["positions"][b] - chk["positions"]).max() < POS_TOL
+        assert np.abs(out["velocities"][b] - chk["velocities"]).max() < POS_TOL
+        assert np.abs(out["final_accelerations"][b] - chk["final_accelerations"]).max() <= 1e-10 * max(
+            np.abs(chk["final_accelerations"]).max(), 1e-300)
+
+
+def test_ensemble_f32_and_leftover_scheduler(engine):
+    """float32 ensemble within 1e-5 of float64; B slightly above the resident grid (home + stolen chunks) and
+    far above it (all tickets) give the same bits as small static batches, with per-system masses."""
+    from hpc.ensemble import simulate_ensemble
+    rng = np.random.RandomState(5)
+    grid = 2 * engine.sm_count
+    for B in (grid + 3, 2 * grid + grid // 2):
+        x0 = rng.rand(B, 48, 3) * 4 - 2
+        v0 = rng.rand(B, 48, 3) - 0.5
+        m = rng.uniform(1e9, 1e10, (B, 48))
+        big = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, n_steps=60, save_interval=5)
+        for lo in (0, B - 50):
+            small = simulate_ensemble(x0[lo:lo + 50], v0[lo:lo + 50], m[lo:lo + 50], dt=1e-3, softening=0.05,
+                                      n_steps=60, save_interval=5)
+            for key in ("positions", "velocities", "accelerations", "final_positions", "final_accelerations"):
+                assert np.array_equal(big[key][lo:lo + 50], small[key]), (B, lo, key)
+    f32 = simulate_ensemble(x0[:8], v0[:8], m[:8], dt=1e-3, softening=0.05, n_steps=60, save_interval=5, dtype="float32")
+    f64 = simulate_ensemble(x0[:8], v0[:8], m[:8], dt=1e-3, softening=0.05, n_steps=60, save_interval=5)
+    assert np.abs(f32["positions"] - f64["positions"]).max() / np.abs(f64["positions"]).max() < 1e-5
