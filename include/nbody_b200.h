@@ -61,7 +61,9 @@ int nb_padded_bodies(int n);
 /* j-segmentation of a system of n bodies: every i sums segment partials in ascending segment
  * order, so the result depends on n only -- not on the slab [i0, i0+n_i) or the rank count. */
 int nb_segment_plan(int n, int* seg_len, int* n_seg);
-/* Bytes of device scratch nb_accel_* / nb_step_* need for a slab of n_i bodies in a system of n. */
+/* Bytes of device scratch nb_accel_* / nb_step_* need for a slab of n_i bodies in a system of n.  The scratch must be
+ * ZERO before the first call that uses it (it ends with one arrival counter per i-tile); every call leaves the counters
+ * zero, so one cudaMemset at allocation time is enough. */
 size_t nb_workspace_bytes(int n, int n_i, int is_f64);
 
 /* ---- layout --------------------------------------------------------------------------------
@@ -89,7 +91,8 @@ int nb_accel_f32(const float* stream, int n, int i0, int n_i, double softening, 
  *
  * nb_kick_drift_*: opening half of a step for the slab: v += (dt/2)*a ; x += dt*v, new positions
  *   written to rows [i0, i0+n_i) of stream_next (:205,:208).
- * nb_step_*: the force pass on stream_cur (positions x_k of all n bodies) fused with the closing
+ * nb_step_*: ONE launch: the force pass on stream_cur (positions x_k of all n bodies); the CTA that completes an
+ *   i-tile last adds the segment partials in order and applies the closing
  *   kick v_k = v + (dt/2)*a_k (:211,:214), the optional snapshot of (x_k, v_k, a_k) into rows
  *   [i0, i0+n_i) of snap_pos/snap_vel/snap_acc (API layout float64, may be NULL), and -- with
  *   NB_STEP_CONTINUE -- the next step's opening kick and drift into stream_next.

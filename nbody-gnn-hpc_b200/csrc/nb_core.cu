@@ -77,7 +77,11 @@ size_t nb_workspace_bytes(int n, int n_i, int is_f64) {
     nb_segment_plan(n, nullptr, &n_seg);
     const size_t elt = is_f64 ? sizeof(double) : sizeof(float);
     size_t bytes = (size_t)n_seg * 3 * (size_t)(n_i > 0 ? n_i : 1) * elt;
-    return (bytes + 255) / 256 * 256;
+    bytes = (bytes + 255) / 256 * 256;
+    // header: one arrival counter per i-tile of the WHOLE system (smallest tile: 128 bodies), so the layout does not
+    // depend on the slab; must be zero before the first launch that uses the workspace -- every launch leaves it zero
+    bytes += (((size_t)(n > 0 ? n : 1) / 128 + 2) * sizeof(int) + 255) / 256 * 256;
+    return bytes;
 }
 
 }  // extern "C"

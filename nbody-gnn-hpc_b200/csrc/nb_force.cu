@@ -8,9 +8,11 @@
 // registers) and one j-segment; the segment is streamed global -> shared memory as 4 KB tiles by
 // 1-D bulk TMA copies (cp.async.bulk, completion on an mbarrier, 4-deep ring), every thread reads
 // each j (pair) with broadcast LDS.128 and applies it to its kP bodies.  Segment partials go to
-// the workspace; nb_finish_* adds them in ascending segment order and, for K2, applies the
-// closing kick, writes the snapshot, applies the next opening kick and drift, and writes the new
-// positions into the other stream buffer -- positions never leave HBM between steps.
+// the workspace; the CTA that arrives LAST at its i-tile's counter (tile_epilogue) adds them in
+// ascending segment order and, for K2, applies the closing kick, writes the snapshot, applies the
+// next opening kick and drift, and writes the new positions into the other stream buffer -- force
+// pass and leapfrog are one launch and positions never leave HBM between steps.  (The sharded
+// peer-store variant keeps its finish in a second kernel, finish_peer_kernel.)
 //
 // float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
 // (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
@@ -107,12 +109,107 @@ __device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stre
     return stream[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
 }
 
+// ------------------------------------------------------------------------------------------------
+// stream access and the per-body finish (ordered segment reduction + leapfrog)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct StreamIO;
+template <>
+struct StreamIO<double> {
+    static __device__ __forceinline__ double get(const double* s, int body, int c) { return s[(size_t)body * 4 + c]; }
+    static __device__ __forceinline__ void put(double* s, int body, int c, double v) { s[(size_t)body * 4 + c] = v; }
+};
+template <>
+struct StreamIO<float> {
+    static __device__ __forceinline__ float get(const float* s, int body, int c) {
+        return s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
+    }
+    static __device__ __forceinline__ void put(float* s, int body, int c, float v) {
+        s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)] = v;
+    }
+};
+
+enum { kEpiNone = 0, kEpiAccel = 1, kEpiStep = 2 };
+
+// What the LAST CTA to finish an i-tile does with the tile's bodies, inside the force kernel itself.
+template <typename T>
+struct Epilogue {
+    int mode;           // kEpiNone: partials only; kEpiAccel: acc = sum; kEpiStep: + kicks, snapshot, drift
+    int n_seg;
+    int* tile_counter;  // one word per i-tile, zero before the launch, left zero
+    const T* cur;
+    T* next;
+    T* vel;
+    T* acc;
+    T dt, half_dt;
+    int flags;
+    double* sp;
+    double* sv;
+    double* sa;
+};
+
+// Body li of the slab: add its segment partials in ascending order, then (kEpiStep) the closing kick, the
+// snapshot row, and with NB_STEP_CONTINUE the next opening kick and the drift into the other stream.
+template <typename T>
+__device__ __forceinline__ void finish_body(const Epilogue<T>& e, const T* partial, int i0, int n_i, int li) {
+    T a[3] = {T(0), T(0), T(0)};
+    for (int s = 0; s < e.n_seg; ++s) {
+        const T* p = partial + (size_t)s * 3 * n_i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[c] += __ldcg(p + (size_t)c * n_i + li);  // written by other CTAs: read at L2
+    }
+    if (e.mode == kEpiAccel) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) e.acc[(size_t)li * 3 + c] = a[c];
+        return;
+    }
+    const int gi = i0 + li;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T x = StreamIO<T>::get(e.cur, gi, c);
+        T v = e.vel[(size_t)li * 3 + c];
+        v = mul_add_unfused(e.half_dt, a[c], v);  // closing kick, nbody.py:214
+        if (e.flags & NB_STEP_SNAPSHOT) {          // get_state(), nbody.py:250-259
+            if (e.sp) e.sp[(size_t)gi * 3 + c] = (double)x;
+            if (e.sv) e.sv[(size_t)gi * 3 + c] = (double)v;
+            if (e.sa) e.sa[(size_t)gi * 3 + c] = (double)a[c];
+        }
+        if (e.flags & NB_STEP_CONTINUE) {
+            v = mul_add_unfused(e.half_dt, a[c], v);  // next step's opening kick, nbody.py:205
+            x = mul_add_unfused(e.dt, v, x);          // drift, nbody.py:208
+            StreamIO<T>::put(e.next, gi, c, x);
+        }
+        e.vel[(size_t)li * 3 + c] = v;
+        e.acc[(size_t)li * 3 + c] = a[c];
+    }
+}
+
+// Called by every thread of a force CTA after its partials are stored.  The CTA that arrives last at its
+// i-tile's counter owns the tile's finish: the force pass and the leapfrog are ONE launch.
+template <typename T, int kP, int kBlock>
+__device__ __forceinline__ void tile_epilogue(const Epilogue<T>& e, const T* partial, int i0, int n_i, int li0) {
+    if (e.mode == kEpiNone) return;
+    __shared__ int s_last;
+    __threadfence();  // this thread's partials are visible device-wide before the arrival count
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(e.tile_counter + blockIdx.x, 1) == (int)gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) e.tile_counter[blockIdx.x] = 0;  // ready for the next launch
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < kP; ++k) {
+        const int li = li0 + k * kBlock;
+        if (li < n_i) finish_body<T>(e, partial, i0, n_i, li);
+    }
+}
+
 // __launch_bounds__(kBlock, 512 / kBlock): two 256-thread (or four 128-thread) CTAs per SM and up to 128
 // registers; without the second argument ptxas settles for 76 registers and a 3% slower schedule.
 template <int kP, int kBlock, bool kZeroEps>
 __global__ void __launch_bounds__(kBlock, 512 / kBlock)
 force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, float eps2,
-                 float* __restrict__ partial, const PeerWait wait) {
+                 float* __restrict__ partial, const PeerWait wait, const Epilogue<float> epi) {
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
     peer_wait(wait);
@@ -179,6 +276,7 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
             out[(size_t)2 * n_i + li] = az[k].x + az[k].y;
         }
     }
+    tile_epilogue<float, kP, kBlock>(epi, partial, i0, n_i, li0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +285,7 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
 template <int kP, int kBlock, bool kZeroEps>
 __global__ void __launch_bounds__(kBlock)
 force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, int seg_len, double eps2,
-                 double* __restrict__ partial, const PeerWait wait) {
+                 double* __restrict__ partial, const PeerWait wait, const Epilogue<double> epi) {
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
     peer_wait(wait);
@@ -232,67 +330,7 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
             out[(size_t)2 * n_i + li] = az[k];
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// finish: ordered segment reduction + (optionally) the leapfrog around it
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-struct StreamIO;
-template <>
-struct StreamIO<double> {
-    static __device__ __forceinline__ double get(const double* s, int body, int c) { return s[(size_t)body * 4 + c]; }
-    static __device__ __forceinline__ void put(double* s, int body, int c, double v) { s[(size_t)body * 4 + c] = v; }
-};
-template <>
-struct StreamIO<float> {
-    static __device__ __forceinline__ float get(const float* s, int body, int c) {
-        return s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
-    }
-    static __device__ __forceinline__ void put(float* s, int body, int c, float v) {
-        s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)] = v;
-    }
-};
-
-// kStep == false: acc = sum of partials (K1).
-// kStep == true : closing kick, snapshot, and with NB_STEP_CONTINUE the next opening kick + drift (K2).
-template <typename T, bool kStep>
-__global__ void __launch_bounds__(256)
-finish_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, const T* __restrict__ stream_cur,
-              T* __restrict__ stream_next, T* __restrict__ vel, T* __restrict__ acc, T dt, T half_dt, int flags,
-              double* __restrict__ snap_pos, double* __restrict__ snap_vel, double* __restrict__ snap_acc) {
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= n_i) return;
-    T a[3] = {T(0), T(0), T(0)};
-    for (int s = 0; s < n_seg; ++s) {
-        const T* p = partial + (size_t)s * 3 * n_i;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) a[c] += p[(size_t)c * n_i + li];
-    }
-    if (!kStep) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[(size_t)li * 3 + c] = a[c];
-        return;
-    }
-    const int gi = i0 + li;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        T x = StreamIO<T>::get(stream_cur, gi, c);
-        T v = vel[(size_t)li * 3 + c];
-        v = mul_add_unfused(half_dt, a[c], v);  // closing kick, nbody.py:214
-        if (flags & NB_STEP_SNAPSHOT) {         // get_state(), nbody.py:250-259
-            if (snap_pos) snap_pos[(size_t)gi * 3 + c] = (double)x;
-            if (snap_vel) snap_vel[(size_t)gi * 3 + c] = (double)v;
-            if (snap_acc) snap_acc[(size_t)gi * 3 + c] = (double)a[c];
-        }
-        if (flags & NB_STEP_CONTINUE) {
-            v = mul_add_unfused(half_dt, a[c], v);  // next step's opening kick, nbody.py:205
-            x = mul_add_unfused(dt, v, x);          // drift, nbody.py:208
-            StreamIO<T>::put(stream_next, gi, c, x);
-        }
-        vel[(size_t)li * 3 + c] = v;
-        acc[(size_t)li * 3 + c] = a[c];
-    }
+    tile_epilogue<double, kP, kBlock>(epi, partial, i0, n_i, li0);
 }
 
 // Bodies per 32-byte stream record.
@@ -464,18 +502,25 @@ struct Tile<double> {
 
 template <int kP, int kBlock, bool kZeroEps>
 static void launch_force(const float* stream, const Slab& sl, float eps2, float* partial, const PeerWait& w,
-                         cudaStream_t st) {
+                         const Epilogue<float>& e, cudaStream_t st) {
     dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
     force_f32_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
-                                                                     partial, w);
+                                                                     partial, w, e);
 }
 template <int kP, int kBlock, bool kZeroEps>
 static void launch_force(const double* stream, const Slab& sl, double eps2, double* partial, const PeerWait& w,
-                         cudaStream_t st) {
+                         const Epilogue<double>& e, cudaStream_t st) {
     dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
     force_f64_kernel<kP, kBlock, kZeroEps><<<grid, kBlock, 0, st>>>(stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len, eps2,
-                                                                     partial, w);
+                                                                     partial, w, e);
 }
+
+// Workspace layout: [i-tile arrival counters, sized by n alone][segment partials of this slab].  The header does
+// not depend on the slab, so one workspace serves calls on different slabs of the same system.
+static size_t counter_bytes(int n) { return (((size_t)n / 128 + 2) * sizeof(int) + 255) / 256 * 256; }
+static int* tile_counters(void* ws) { return static_cast<int*>(ws); }
+template <typename T>
+static T* partials(void* ws, int n) { return reinterpret_cast<T*>(static_cast<char*>(ws) + counter_bytes(n)); }
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -489,8 +534,9 @@ static int sm_count() {
 }
 
 template <typename T>
-static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st,
+static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st, Epilogue<T> e,
                       const PeerWait& w = PeerWait{nullptr, 0, 0}) {
+    e.n_seg = sl.n_seg;
     const T eps2 = (T)(softening * softening);
     const bool zero = !(eps2 > T(0));
     using TL = Tile<T>;
@@ -498,11 +544,11 @@ static int force_pass(const T* stream, const Slab& sl, double softening, T* part
     const long ctas_big = (long)ceil_div(sl.n_i, TL::kPBig * TL::kBlockBig) * sl.n_seg;
     const bool big = ctas_big >= 4L * sm_count();
     if (big) {
-        if (zero) launch_force<TL::kPBig, TL::kBlockBig, true>(stream, sl, eps2, partial, w, st);
-        else launch_force<TL::kPBig, TL::kBlockBig, false>(stream, sl, eps2, partial, w, st);
+        if (zero) launch_force<TL::kPBig, TL::kBlockBig, true>(stream, sl, eps2, partial, w, e, st);
+        else launch_force<TL::kPBig, TL::kBlockBig, false>(stream, sl, eps2, partial, w, e, st);
     } else {
-        if (zero) launch_force<TL::kPSmall, TL::kBlockSmall, true>(stream, sl, eps2, partial, w, st);
-        else launch_force<TL::kPSmall, TL::kBlockSmall, false>(stream, sl, eps2, partial, w, st);
+        if (zero) launch_force<TL::kPSmall, TL::kBlockSmall, true>(stream, sl, eps2, partial, w, e, st);
+        else launch_force<TL::kPSmall, TL::kBlockSmall, false>(stream, sl, eps2, partial, w, e, st);
     }
     return check_launch("force kernel");
 }
@@ -515,11 +561,12 @@ static int accel_impl(const T* stream, int n, int i0, int n_i, double softening,
     NB_REQUIRE(stream && acc && ws, "null pointer argument");
     NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
                nb_workspace_bytes(n, n_i, sizeof(T) == 8));
-    T* partial = static_cast<T*>(ws);
-    if (int rc = force_pass<T>(stream, sl, softening, partial, st)) return rc;
-    finish_kernel<T, false><<<ceil_div(n_i, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, nullptr, nullptr, nullptr,
-                                                                 acc, T(0), T(0), 0, nullptr, nullptr, nullptr);
-    return check_launch("finish kernel");
+    T* partial = partials<T>(ws, n);
+    Epilogue<T> e{};
+    e.mode = kEpiAccel;
+    e.tile_counter = tile_counters(ws);
+    e.acc = acc;
+    return force_pass<T>(stream, sl, softening, partial, st, e);
 }
 
 template <typename T>
@@ -531,12 +578,15 @@ static int step_impl(const T* cur, T* next, T* vel, T* acc, int n, int i0, int n
     NB_REQUIRE(!(flags & NB_STEP_CONTINUE) || next, "NB_STEP_CONTINUE needs stream_next");
     NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
                nb_workspace_bytes(n, n_i, sizeof(T) == 8));
-    T* partial = static_cast<T*>(ws);
-    if (int rc = force_pass<T>(cur, sl, softening, partial, st)) return rc;
+    T* partial = partials<T>(ws, n);
     const double half_dt = 0.5 * dt;  // "0.5 * self.dt" is evaluated first, nbody.py:205
-    finish_kernel<T, true><<<ceil_div(n_i, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, next, vel, acc, (T)dt,
-                                                                (T)half_dt, flags, sp, sv, sa);
-    return check_launch("finish kernel");
+    Epilogue<T> e{};
+    e.mode = kEpiStep;
+    e.tile_counter = tile_counters(ws);
+    e.cur = cur; e.next = next; e.vel = vel; e.acc = acc;
+    e.dt = (T)dt; e.half_dt = (T)half_dt; e.flags = flags;
+    e.sp = sp; e.sv = sv; e.sa = sa;
+    return force_pass<T>(cur, sl, softening, partial, st, e);
 }
 
 template <typename T>
@@ -560,8 +610,8 @@ static int step_peer_impl(const T* cur, void* const* next_peers, void* const* fl
     }
     tg.n_ranks = n_ranks; tg.my_rank = my_rank; tg.seq = signal_seq;
     PeerWait w{wait_seq ? tg.flags[my_rank] : nullptr, n_ranks, wait_seq};
-    T* partial = static_cast<T*>(ws);
-    if (int rc = force_pass<T>(cur, sl, softening, partial, st, w)) return rc;
+    T* partial = partials<T>(ws, n);
+    if (int rc = force_pass<T>(cur, sl, softening, partial, st, Epilogue<T>{}, w)) return rc;
     const double half_dt = 0.5 * dt;
     const int units = ceil_div(n_i, Record<T>::kBodies);
     finish_peer_kernel<T><<<ceil_div(units, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, vel, acc, (T)dt,

@@ -112,6 +112,7 @@ static int host_accel(const double* pos, const void* masses, int masses_are_f32,
     NB_TRY(ar.alloc(&d_stream, (size_t)n_pad * 4));
     NB_TRY(ar.alloc(&d_acc, n3));
     NB_TRY(ar.alloc((char**)&d_ws, wb));
+    NB_CUDA_OK(cudaMemsetAsync(d_ws, 0, wb, ar.stream));  // i-tile arrival counters start at zero
     NB_TRY(upload_masses(ar, masses, masses_are_f32, n, &d_m));
     NB_CUDA_OK(cudaMemcpyAsync(d_pos, pos, n3 * sizeof(double), cudaMemcpyHostToDevice, ar.stream));
     NB_TRY(Abi<T>::pack(d_pos, d_m, masses_are_f32, n, d_stream, ar.stream));
@@ -144,6 +145,7 @@ static int host_run(double* pos, double* vel, double* acc, const void* masses, i
     NB_TRY(ar.alloc(&d_vel, n3));
     NB_TRY(ar.alloc(&d_acc, n3));
     NB_TRY(ar.alloc((char**)&d_ws, wb));
+    NB_CUDA_OK(cudaMemsetAsync(d_ws, 0, wb, ar.stream));  // i-tile arrival counters start at zero
     if (snaps) {
         NB_TRY(ar.alloc(&d_sp, n_snap * n3));
         NB_TRY(ar.alloc(&d_sv, n_snap * n3));

@@ -205,9 +205,11 @@ class Engine:
         return a.value, b.value
 
     def workspace(self, n: int, n_i: int, dtype):
+        """Scratch for nb_accel_* / nb_step_*: zeroed once (the i-tile arrival counters behind the partials must
+        start at zero; every launch leaves them zero)."""
         torch = _torch()
         nbytes = int(self.lib.nb_workspace_bytes(int(n), int(n_i), int(np.dtype(dtype) == np.float64)))
-        return torch.empty(nbytes, dtype=torch.uint8, device=self.device), nbytes
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device), nbytes
 
     # ---- device-level operations (tensors in, tensors out; used by nbody.py and sharded.py) ----
     def pack(self, pos_dev, masses_dev, masses_f32: int, n: int, dtype, out=None):

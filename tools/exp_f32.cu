@@ -131,7 +131,7 @@ void bench_lib(const char* tag) {
     float best = 1e30f;
     for (int r = 0; r < 6; ++r) {
         cudaEventRecord(e0);
-        k<<<grid, kBlock>>>(d_stream, N, 0, N, SEGLEN, 1e-4f, d_partial, nb::PeerWait{nullptr, 0, 0});
+        k<<<grid, kBlock>>>(d_stream, N, 0, N, SEGLEN, 1e-4f, d_partial, nb::PeerWait{nullptr, 0, 0}, nb::Epilogue<float>{});
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (r > 1 && ms < best) best = ms;
     }
