@@ -113,12 +113,13 @@ int nb_step_f32(const float* stream_cur, float* stream_next, float* vel, float* 
                 void* workspace, size_t workspace_bytes, nb_stream_t s);
 
 /* nb_step_* fused with its collective, for one system sharded by i-slab over the GPUs of a box (no
- * counterpart in the reference, which is single-host).  Same arithmetic as nb_step_*, but the drift stores the
- * slab's new positions directly into the next-stream buffer of EVERY rank over NVLink (peer pointers from
- * symmetric / IPC-mapped memory), and ordering between ranks is carried by arrival words instead of a collective:
+ * counterpart in the reference, which is single-host).  ONE launch, same arithmetic as nb_step_*: the i-tile
+ * epilogue stores the slab's drifted stream records directly into the next-stream buffer of EVERY rank over NVLink
+ * (peer pointers from symmetric / IPC-mapped memory) while other tiles are still computing, and ordering between
+ * ranks is carried by arrival words that the launch's last tile exchanges, instead of a collective call:
  *   next_peers[r]   rank r's next-stream buffer (device pointer valid on this GPU), r = 0..n_ranks-1, own included
- *   flag_peers[r]   rank r's flag array: >= 64 uint32, zero before first use; word q = last sequence number rank q
- *                   published to rank r, word 32 = scratch counter of rank r's own kernels
+ *   flag_peers[r]   rank r's flag array: >= 16 uint32, zero before first use; word q = last sequence number rank q
+ *                   published to rank r
  *   wait_seq        the force pass reads stream_cur only after every rank has published >= wait_seq here (0: no wait)
  *   signal_seq      published to every rank once this rank's whole slab has been stored (> 0, increasing per step)
  *   NB_STEP_PEER_SYNC in flags: the call additionally waits (on the device, in its last thread block) until every

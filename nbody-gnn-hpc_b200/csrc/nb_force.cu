@@ -11,8 +11,10 @@
 // the workspace; the CTA that arrives LAST at its i-tile's counter (tile_epilogue) adds them in
 // ascending segment order and, for K2, applies the closing kick, writes the snapshot, applies the
 // next opening kick and drift, and writes the new positions into the other stream buffer -- force
-// pass and leapfrog are one launch and positions never leave HBM between steps.  (The sharded
-// peer-store variant keeps its finish in a second kernel, finish_peer_kernel.)
+// pass and leapfrog are one launch and positions never leave HBM between steps.  In the sharded
+// mode (nb_step_peer_*) the same epilogue stores the drifted records straight into every rank's
+// next stream over NVLink, tile by tile while other tiles still compute, and the last tile of the
+// launch exchanges arrival words with the peers: force, leapfrog and collective are ONE kernel.
 //
 // float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
 // (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
@@ -63,7 +65,6 @@ __device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int t
 // cross-GPU ordering for the sharded mode (nb_step_peer_*): arrival words in peer-visible memory
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
-constexpr int kCounterSlot = 32;  // word of the local flag array used as the finish kernel's block counter
 
 struct PeerWait {          // force pass: do not read the stream before every rank has published wait_seq
     const uint32_t* flags;  // local array, one word per rank (null: no wait)
@@ -129,14 +130,17 @@ struct StreamIO<float> {
     }
 };
 
-enum { kEpiNone = 0, kEpiAccel = 1, kEpiStep = 2 };
+enum { kEpiNone = 0, kEpiAccel = 1, kEpiStep = 2, kEpiStepPeer = 3 };
 
 // What the LAST CTA to finish an i-tile does with the tile's bodies, inside the force kernel itself.
 template <typename T>
 struct Epilogue {
-    int mode;           // kEpiNone: partials only; kEpiAccel: acc = sum; kEpiStep: + kicks, snapshot, drift
+    int mode;           // kEpiNone: partials only; kEpiAccel: acc = sum; kEpiStep: + kicks, snapshot, drift;
+                        // kEpiStepPeer: the drifted records go to every rank's stream + arrival words
     int n_seg;
     int* tile_counter;  // one word per i-tile, zero before the launch, left zero
+    int* done_counter;  // kEpiStepPeer: finished i-tiles of this launch, zero before, left zero
+    PeerTargets peers;  // kEpiStepPeer only
     const T* cur;
     T* next;
     T* vel;
@@ -151,7 +155,8 @@ struct Epilogue {
 // Body li of the slab: add its segment partials in ascending order, then (kEpiStep) the closing kick, the
 // snapshot row, and with NB_STEP_CONTINUE the next opening kick and the drift into the other stream.
 template <typename T>
-__device__ __forceinline__ void finish_body(const Epilogue<T>& e, const T* partial, int i0, int n_i, int li) {
+__device__ __forceinline__ void finish_body(const Epilogue<T>& e, const T* partial, int i0, int n_i, int li,
+                                            T x_out[3]) {
     T a[3] = {T(0), T(0), T(0)};
     for (int s = 0; s < e.n_seg; ++s) {
         const T* p = partial + (size_t)s * 3 * n_i;
@@ -177,10 +182,38 @@ __device__ __forceinline__ void finish_body(const Epilogue<T>& e, const T* parti
         if (e.flags & NB_STEP_CONTINUE) {
             v = mul_add_unfused(e.half_dt, a[c], v);  // next step's opening kick, nbody.py:205
             x = mul_add_unfused(e.dt, v, x);          // drift, nbody.py:208
-            StreamIO<T>::put(e.next, gi, c, x);
+            if (e.mode == kEpiStep) StreamIO<T>::put(e.next, gi, c, x);
         }
+        x_out[c] = x;
         e.vel[(size_t)li * 3 + c] = v;
         e.acc[(size_t)li * 3 + c] = a[c];
+    }
+}
+
+// Store one 32-byte stream record into the next stream of every rank (two 16-byte stores per peer over NVLink).
+template <typename V>
+__device__ __forceinline__ void store_record_to_peers(const PeerTargets& peers, size_t rec16, V lo, V hi) {
+    for (int p = 0; p < peers.n_ranks; ++p) {
+        V* dst = reinterpret_cast<V*>(peers.next[p]) + rec16;
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+}
+__device__ __forceinline__ void peer_records(const Epilogue<double>& e, int gi, bool valid, const double x[3]) {
+    if (valid && (e.flags & NB_STEP_CONTINUE)) {
+        const double gm = e.cur[(size_t)gi * 4 + 3];
+        store_record_to_peers<double2>(e.peers, (size_t)gi * 2, make_double2(x[0], x[1]), make_double2(x[2], gm));
+    }
+}
+__device__ __forceinline__ void peer_records(const Epilogue<float>& e, int gi, bool valid, const float x[3]) {
+    // a record holds the pair (even body, odd body): the even lane collects its neighbour's new position
+    const float x1 = __shfl_down_sync(0xffffffffu, x[0], 1);
+    const float y1 = __shfl_down_sync(0xffffffffu, x[1], 1);
+    const float z1 = __shfl_down_sync(0xffffffffu, x[2], 1);
+    if (valid && !(gi & 1) && (e.flags & NB_STEP_CONTINUE)) {
+        const float4 b = reinterpret_cast<const float4*>(e.cur)[(size_t)gi + 1];  // z0 z1 gm0 gm1 of this pair
+        store_record_to_peers<float4>(e.peers, (size_t)gi, make_float4(x[0], x1, x[1], y1),
+                                      make_float4(x[2], z1, b.z, b.w));
     }
 }
 
@@ -200,7 +233,33 @@ __device__ __forceinline__ void tile_epilogue(const Epilogue<T>& e, const T* par
 #pragma unroll
     for (int k = 0; k < kP; ++k) {
         const int li = li0 + k * kBlock;
-        if (li < n_i) finish_body<T>(e, partial, i0, n_i, li);
+        const bool valid = li < n_i;
+        T x[3] = {T(0), T(0), T(0)};  // lanes past the slab stand for padding bodies (position 0, G*m 0)
+        if (valid) finish_body<T>(e, partial, i0, n_i, li, x);
+        if (e.mode == kEpiStepPeer) peer_records(e, i0 + li, valid, x);
+    }
+    if (e.mode != kEpiStepPeer) return;
+    // K2 fused with its collective.  This tile's records are on their way to every rank; when the LAST tile of
+    // the launch gets here, one thread per peer publishes this rank's arrival word there and (NB_STEP_PEER_SYNC)
+    // waits for that peer's word here, so the kernel boundary orders the next force pass after every rank's stores.
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(e.done_counter, 1) == (int)gridDim.x - 1;
+        if (s_last) *e.done_counter = 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < e.peers.n_ranks) {
+        __threadfence_system();
+        st_release_sys(e.peers.flags[threadIdx.x] + e.peers.my_rank, e.peers.seq);
+        if (e.flags & NB_STEP_PEER_SYNC) {
+            const uint32_t* mine = e.peers.flags[e.peers.my_rank] + threadIdx.x;
+            long long spins = 0;
+            while ((int32_t)(ld_acquire_sys(mine) - e.peers.seq) < 0) {
+                __nanosleep(50);
+                if (++spins > (1LL << 27)) break;  // a peer died; do not hang the GPU
+            }
+        }
     }
 }
 
@@ -331,93 +390,6 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
         }
     }
     tile_epilogue<double, kP, kBlock>(epi, partial, i0, n_i, li0);
-}
-
-// Bodies per 32-byte stream record.
-template <typename T> struct Record;
-template <> struct Record<double> { static constexpr int kBodies = 1; };
-template <> struct Record<float> { static constexpr int kBodies = 2; };
-
-// K2 fused with its collective: the same reduction + leapfrog as finish_kernel<T, true>, but a thread owns one
-// whole 32-byte stream record (one body in float64, a pair in float32) and stores the drifted record straight
-// into the next-stream buffer of EVERY rank (two 16-byte stores per peer over NVLink, consecutive threads ->
-// consecutive records).  When the last block of the grid is done, one thread publishes this rank's arrival word
-// on every rank; the peers' next force pass waits on those words (peer_wait) instead of on an NCCL all-gather.
-template <typename T>
-__global__ void __launch_bounds__(256)
-finish_peer_kernel(const T* __restrict__ partial, int n_seg, int i0, int n_i, const T* __restrict__ stream_cur,
-                   T* __restrict__ vel, T* __restrict__ acc, T dt, T half_dt, int flags, double* __restrict__ snap_pos,
-                   double* __restrict__ snap_vel, double* __restrict__ snap_acc, const PeerTargets peers) {
-    constexpr int kB = Record<T>::kBodies;
-    using V = typename std::conditional<sizeof(T) == 8, double2, float4>::type;  // 16 bytes
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;  // record index within the slab (i0 is a multiple of 32)
-    const int n_units = (n_i + kB - 1) / kB;
-    if (u < n_units) {
-        const size_t rec = (size_t)(i0 / kB + u) * 2;  // in 16-byte units
-        V lo = reinterpret_cast<const V*>(stream_cur)[rec];
-        V hi = reinterpret_cast<const V*>(stream_cur)[rec + 1];
-        T* w = reinterpret_cast<T*>(&lo);   // float64: x y | z gm      float32: x0 x1 y0 y1 | z0 z1 gm0 gm1
-        T* wh = reinterpret_cast<T*>(&hi);
-#pragma unroll
-        for (int b = 0; b < kB; ++b) {
-            const int li = u * kB + b;
-            if (li >= n_i) break;
-            const int gi = i0 + li;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                T a = T(0);
-                for (int sg = 0; sg < n_seg; ++sg) a += partial[((size_t)sg * 3 + c) * n_i + li];
-                T* slot = (sizeof(T) == 8) ? (c < 2 ? w + c : wh) : (c < 2 ? w + 2 * c + b : wh + b);
-                T x = *slot;
-                T v = vel[(size_t)li * 3 + c];
-                v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
-                if (flags & NB_STEP_SNAPSHOT) {
-                    if (snap_pos) snap_pos[(size_t)gi * 3 + c] = (double)x;
-                    if (snap_vel) snap_vel[(size_t)gi * 3 + c] = (double)v;
-                    if (snap_acc) snap_acc[(size_t)gi * 3 + c] = (double)a;
-                }
-                if (flags & NB_STEP_CONTINUE) {
-                    v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
-                    x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
-                    *slot = x;
-                }
-                vel[(size_t)li * 3 + c] = v;
-                acc[(size_t)li * 3 + c] = a;
-            }
-        }
-        if (flags & NB_STEP_CONTINUE) {
-            for (int p = 0; p < peers.n_ranks; ++p) {
-                V* dst = reinterpret_cast<V*>(peers.next[p]) + rec;
-                dst[0] = lo;
-                dst[1] = hi;
-            }
-        }
-    }
-    __threadfence_system();  // this thread's peer stores are ordered before the arrival word
-    __syncthreads();
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-        unsigned* counter = reinterpret_cast<unsigned*>(peers.flags[peers.my_rank] + kCounterSlot);
-        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;  // last block of this rank
-        if (s_last) {
-            *counter = 0;
-            __threadfence_system();
-        }
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x < peers.n_ranks) {
-        // one thread per peer: publish this rank's arrival there, then (NB_STEP_PEER_SYNC) wait for that peer's
-        // arrival here, so the kernel boundary alone orders the next force pass after every rank's stores
-        st_release_sys(peers.flags[threadIdx.x] + peers.my_rank, peers.seq);
-        if (flags & NB_STEP_PEER_SYNC) {
-            const uint32_t* mine = peers.flags[peers.my_rank] + threadIdx.x;
-            long long spins = 0;
-            while ((int32_t)(ld_acquire_sys(mine) - peers.seq) < 0) {
-                __nanosleep(50);
-                if (++spins > (1LL << 27)) break;  // a peer died; do not hang the GPU
-            }
-        }
-    }
 }
 
 template <typename T>
@@ -611,12 +583,16 @@ static int step_peer_impl(const T* cur, void* const* next_peers, void* const* fl
     tg.n_ranks = n_ranks; tg.my_rank = my_rank; tg.seq = signal_seq;
     PeerWait w{wait_seq ? tg.flags[my_rank] : nullptr, n_ranks, wait_seq};
     T* partial = partials<T>(ws, n);
-    if (int rc = force_pass<T>(cur, sl, softening, partial, st, Epilogue<T>{}, w)) return rc;
     const double half_dt = 0.5 * dt;
-    const int units = ceil_div(n_i, Record<T>::kBodies);
-    finish_peer_kernel<T><<<ceil_div(units, 256), 256, 0, st>>>(partial, sl.n_seg, i0, n_i, cur, vel, acc, (T)dt,
-                                                                  (T)half_dt, flags, sp, sv, sa, tg);
-    return check_launch("finish_peer kernel");
+    Epilogue<T> e{};
+    e.mode = kEpiStepPeer;
+    e.tile_counter = tile_counters(ws);
+    e.done_counter = tile_counters(ws) + (n / 128 + 1);
+    e.peers = tg;
+    e.cur = cur; e.vel = vel; e.acc = acc;
+    e.dt = (T)dt; e.half_dt = (T)half_dt; e.flags = flags;
+    e.sp = sp; e.sv = sv; e.sa = sa;
+    return force_pass<T>(cur, sl, softening, partial, st, e, w);
 }
 
 template <typename T>
