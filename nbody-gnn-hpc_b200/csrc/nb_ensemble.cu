@@ -4,29 +4,45 @@
 // scripts/generate_data.py:32-58,142-149: there each worker builds one NBodySimulator and calls
 // run(n_steps) (src/hpc/nbody.py:220-248), i.e. n_steps x [step() + get_state()].
 //
-// One CTA owns one system for a range of steps; the whole state lives in shared memory:
+// A system being advanced lives in shared memory:
 //   pos   N x {x,y,z,G*m}      read by every thread in the force phase (broadcast LDS.128)
 //   vel, acc   3N each          the integrator's state, (body, component) order = API order
 //   part  parts x 3N            force partials, one slab per j-part
-//   stage 3 x 3N                the snapshot row (x_k, v_k, a_k) waiting to be streamed out
-// A step is two phases separated by two CTA barriers:
+// A step of one system is two phases:
 //   F  every thread owns TWO bodies (r, r + rows) and one of `parts` contiguous j ranges: 2
-//      independent interaction chains per loaded j.  Before its force loop the thread streams its
-//      share of the previous step's snapshot row from `stage` to HBM -- consecutive 8-byte words,
-//      fully coalesced, in the reference's (T+1, N, 3) layout, overlapped with the arithmetic.
-//   I  the 3N (body, component) scalars are spread over all threads: partials added in ascending
-//      part order, closing kick, snapshot into `stage`, next opening kick and drift.
-// For N = 200 this is 100 rows x 5 parts = 500 threads -> 16 warps, four per scheduler, two CTAs
-// per SM: the four FP64 pipes of an SM carry equal load (13-warp CTAs lost 20% to that skew).
+//      independent interaction chains per loaded j.  N = 200: 100 rows x 5 parts = 500 threads, 16
+//      warps, four per scheduler, so the four FP64 pipes of the SM carry equal load.
+//   I  the 3N (body, component) scalars are spread over all threads (a thread keeps the same scalars
+//      for the whole launch; their offsets are computed once): partials added in ascending part
+//      order, closing kick, snapshot row stored straight to HBM -- consecutive threads store
+//      consecutive 8-byte words of the reference's (T+1, N, 3) layout --, next opening kick, drift.
+// F needs every thread's I of the previous step and I needs every thread's F: two CTA-wide
+// dependencies per step, and phase I is a latency-bound sliver (25 dependent FP64 operations) during
+// which the FP64 pipe idles.
 //
-// Scheduling.  The grid is persistent: at most (resident CTAs per SM) x (SM count) CTAs.  Whole
-// grid-rounds of systems are "home" systems: a CTA keeps its system in shared memory from the first
-// step to the last.  The B mod grid leftover systems (4 of 300 on 148 SMs) advance in step chunks
-// that home CTAs steal at their own (staggered) step boundaries -- (chunk, system) tickets from a
-// global counter, chunk-major; a system's state is handed from chunk to chunk through the in/out
-// state arrays and a per-system progress word.  With many leftovers every system advances by
-// tickets.  A ticket's predecessor always has a lower ticket number, hence a CTA that is already
-// running, so the waits cannot deadlock.  This removes the 300-systems-on-148-SMs tail.
+// Two lanes and integrator warps.  ONE CTA per SM advances TWO systems, "lanes".  Its 16 force
+// warps run  F(0) F(1) F(0) F(1) ...  without ever meeting at a CTA barrier; four more warps do
+// nothing but phase I: I(0) while the force warps are in F(1), I(1) while they are in F(0).  The
+// dependencies are mbarriers with split arrive / wait: a force warp arrives on "F(L) done" (count:
+// force warps) and moves on; the integrators wait for it, integrate lane L, and arrive on "I(L)
+// done" (count: integrator warps), which the force warps only look at a whole force phase later.  The FP64 pipe never drains at a barrier and phase I is off the critical path: a step
+// costs its force phase.  With fewer systems than 2 x SMs there is one lane and every thread takes
+// part in both phases (same barriers, counts = all warps).
+// (Two co-resident 512-thread CTAs were the earlier way to overlap the phases.  Measured with
+// tools/exp_ens.cu: the SM favours the CTA that arrived first -- it finishes 400 steps in 3.1 ms,
+// its neighbour in 5.3 ms -- so CTAs advance at unpredictable rates and any work sharing between
+// them stalls; and with both lanes integrated by all warps in lock step nothing overlaps either:
+// 5.42 ms against 5.57 ms for 296 systems; profiles/r01_exp_ens_*.log.)
+//
+// Scheduling.  The grid is persistent, one CTA per SM, `lanes` workers per CTA.  The B x n_steps
+// system-steps of the launch are laid on one line, system-major, and cut into equal intervals, one
+// per worker.  A system that straddles a cut is shared by two neighbouring workers: worker w runs
+// its first steps ("head") BEFORE anything else and parks the state in the in/out arrays behind a
+// per-system flag; worker w+1 runs the remaining steps ("tail") AFTER everything else of its own.
+// An interval is at least one whole system long, so the head has been done for a whole system's
+// time when the tail is wanted: all workers advance in lock step (same code, one CTA per SM), so
+// nobody waits, every worker gets the same work to within one step, and 300 systems on 296 workers
+// cost 300/296 of 296 systems (measured: 5.72 -> 5.80 ms) instead of a second round.
 #include "nb_common.cuh"
 
 namespace nb {
@@ -78,13 +94,9 @@ struct EnsembleArgs {
     int n_snap_total, snap_offset;
     int rows;         // threads per part; a thread owns bodies r and r + rows
     int parts;        // j-parts
-    int chunk_steps;  // steps per leftover ticket
-    int n_chunks;
-    int* sm_slots;    // per-SM arrival counter (zero on entry) used to stagger co-resident CTAs, or null
-    unsigned stagger_ns;  // delay of every second CTA of an SM, about half a step
-    int home_rounds;  // whole grid-rounds of systems that stay resident in their CTA (0: everything by ticket)
-    int* ticket;      // ticket mode: global ticket counter, zero on entry
-    int* progress;    // ticket mode: per-system count of finished chunks, zero on entry
+    int lanes;        // systems advanced side by side by one CTA (1 or 2)
+    int f_threads;    // threads that run phase F; blockDim.x - f_threads (0 or 128) threads only integrate
+    int* progress;    // per-system flag, zero on entry: 1 once the head steps of a shared system are parked
 };
 
 template <typename T>
@@ -93,275 +105,345 @@ struct SystemSmem {
     T* vel;
     T* acc;
     T* part;
-    T* stage;  // x | v | a, 3N each
 };
 
+// shared memory of one lane, rounded to 16 bytes
 template <typename T>
-__host__ __device__ inline size_t ensemble_smem_bytes(int N, int parts) {
-    return (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(2 + parts + 3) * 3 * N * sizeof(T);
+__host__ __device__ inline size_t lane_smem_bytes(int N, int parts) {
+    const size_t b = (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(2 + parts) * 3 * N * sizeof(T);
+    return (b + 15) / 16 * 16;
 }
 
-// Stream the staged snapshot row to HBM: 3 x 3N consecutive doubles, coalesced.
-template <typename T>
-__device__ __forceinline__ void flush_stage(const EnsembleArgs& g, const SystemSmem<T>& s, int b, long srow) {
-    const int n3 = 3 * g.N;
-    const size_t o = ((size_t)b * g.n_snap_total + (size_t)srow) * n3;
-    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
-        g.out_x[o + idx] = (double)s.stage[idx];
-        g.out_v[o + idx] = (double)s.stage[n3 + idx];
-        g.out_a[o + idx] = (double)s.stage[2 * n3 + idx];
+// Thread shape for N bodies: two bodies per thread, as many j-parts as fit in 512 threads (at most 8).
+__host__ __device__ constexpr int shape_rows(int N) { return (N + 1) / 2; }
+__host__ __device__ constexpr int shape_parts(int N) {
+    int p = 512 / shape_rows(N);
+    p = p < 1 ? 1 : p;
+    p = p > 8 ? 8 : p;
+    return p > N ? N : p;
+}
+
+// Which integrator scalars (body, component) a thread owns: idx = first + e * stride over the integrating threads.
+// The first two are kept in registers for the whole launch; any further ones are recomputed on the fly.  The same
+// thread loads, integrates and stores a scalar, so none of that needs a barrier.
+struct Owned {
+    int idx[2];   // API-order index 3*i + c, or -1
+    int poff[2];  // offset of the coordinate inside pos (4*i + c)
+    int first, stride;
+};
+__device__ __forceinline__ Owned make_owned(int n3, int first, int stride) {
+    Owned o;
+    o.first = first; o.stride = stride;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int idx = first + e * stride;
+        const int i = idx / 3;
+        o.idx[e] = idx < n3 ? idx : -1;
+        o.poff[e] = idx < n3 ? 4 * i + (idx - 3 * i) : 0;
+    }
+    return o;
+}
+template <class F>
+__device__ __forceinline__ void for_each_owned(const Owned& own, int n3, F&& f) {
+    if (own.idx[0] >= 0) f(own.idx[0], own.poff[0]);
+    if (own.idx[1] >= 0) f(own.idx[1], own.poff[1]);
+#pragma unroll 4
+    for (int idx = own.first + 2 * own.stride; idx < n3; idx += own.stride) {
+        const int i = idx / 3;
+        f(idx, 4 * i + (idx - 3 * i));
     }
 }
 
-// Global state of system b -> shared memory (synchronised state of some step k).
+// One piece of work of a worker: system b from the synchronised state of step k0 to that of step k1.
+struct Piece {
+    int b, k0, k1;
+    bool wait;     // the state of step k0 was parked by the previous worker: wait for its flag
+    bool publish;  // park the state of step k1 for the next worker and raise the flag
+};
+
+// A worker's interval [lo, hi) of the B x n system-step line, as the ordered list: head of the system shared with
+// the next worker, whole systems, tail of the system shared with the previous worker (see the header).
+struct Worker {
+    int b_first, s_first, b_last, s_last, b_whole, n_steps, stage;
+    __device__ void init(long w, long n_workers, int B, int n_steps_) {
+        n_steps = n_steps_;
+        const long n = n_steps_ > 0 ? n_steps_ : 1;  // n_steps == 0 (a_0 / first snapshot only): one unit per system
+        const long W = (long)B * n;
+        const long lo = w * W / n_workers, hi = (w + 1) * W / n_workers;
+        b_first = (int)(lo / n); s_first = (int)(lo - (long)b_first * n);
+        b_last = (int)(hi / n);  s_last = (int)(hi - (long)b_last * n);
+        b_whole = b_first + (s_first > 0 ? 1 : 0);
+        stage = 0;
+    }
+    __device__ bool next(Piece& p) {
+        if (stage == 0) {
+            stage = 1;
+            if (s_last > 0) { p = Piece{b_last, 0, s_last, false, true}; return true; }
+        }
+        if (stage == 1) {
+            if (b_whole < b_last) { p = Piece{b_whole++, 0, n_steps, false, false}; return true; }
+            stage = 2;
+        }
+        if (stage == 2) {
+            stage = 3;
+            if (s_first > 0) { p = Piece{b_first, s_first, n_steps, true, false}; return true; }
+        }
+        return false;
+    }
+};
+
+// mbarrier wait that traps instead of hanging the GPU if the other warps never arrive (a bug, not a load effect)
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    unsigned spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    } while (!done);
+}
+// one arrival per warp, after the whole warp's shared-memory accesses
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Global state of system p.b -> the lane's shared memory, by the owner threads (no barrier needed).
 template <typename T>
-__device__ __forceinline__ void load_state(const EnsembleArgs& g, int b, const SystemSmem<T>& s) {
-    const int N = g.N, n3 = 3 * N;
-    const int tid = threadIdx.x;
-    const size_t sbase = (size_t)b * n3;
+__device__ __forceinline__ void load_piece(const EnsembleArgs& g, const Piece& p, const SystemSmem<T>& s,
+                                           const Owned& own, int N) {
+    const int n3 = 3 * N;
+    const size_t sbase = (size_t)p.b * n3;
     T* pos_s = reinterpret_cast<T*>(s.pos);
-    __syncthreads();  // the previous system's readers are done with the shared state
-    for (int idx = tid; idx < n3; idx += blockDim.x) {
-        // L2 loads: another SM may have written this state a chunk ago
-        const int i = idx / 3, c = idx - 3 * i;
-        pos_s[4 * i + c] = (T)__ldcg(&g.x[sbase + idx]);
+    if (p.wait) {  // every thread polls for itself: its own loads below are ordered after the flag
+        volatile int* flag = g.progress + p.b;
+        unsigned spins = 0;
+        while (*flag == 0) {
+            __nanosleep(64);
+            if (++spins > (1u << 26)) __trap();  // the previous worker died
+        }
+        __threadfence();
+    }
+    for_each_owned(own, n3, [&](int idx, int poff) {
+        pos_s[poff] = (T)__ldcg(&g.x[sbase + idx]);  // L2 loads: another SM may have parked this state
         s.vel[idx] = (T)__ldcg(&g.v[sbase + idx]);
         s.acc[idx] = (T)__ldcg(&g.a[sbase + idx]);
-    }
-    for (int i = tid; i < N; i += blockDim.x) {
-        const size_t mi = (size_t)b * g.mass_stride + i;
+    });
+    for (int i = own.first; i < N; i += own.stride) {
+        const size_t mi = (size_t)p.b * g.mass_stride + i;
         const double m = g.masses_are_f32 ? (double)static_cast<const float*>(g.masses)[mi]
                                           : static_cast<const double*>(g.masses)[mi];
         pos_s[4 * i + 3] = (T)(kG * m);  // G * masses[j], nbody.py:57
     }
-    __syncthreads();
 }
 
-// Shared memory -> global state of system b, published for other CTAs.
+// The lane's shared memory -> global state of system b, by the owner threads.
 template <typename T>
-__device__ __forceinline__ void store_state(const EnsembleArgs& g, int b, const SystemSmem<T>& s) {
-    const int n3 = 3 * g.N;
+__device__ __forceinline__ void store_piece(const EnsembleArgs& g, int b, const SystemSmem<T>& s, const Owned& own,
+                                            int N) {
+    const int n3 = 3 * N;
     const size_t sbase = (size_t)b * n3;
     const T* pos_s = reinterpret_cast<const T*>(s.pos);
-    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
-        const int i = idx / 3, c = idx - 3 * i;
-        g.x[sbase + idx] = (double)pos_s[4 * i + c];
+    for_each_owned(own, n3, [&](int idx, int poff) {
+        g.x[sbase + idx] = (double)pos_s[poff];
         g.v[sbase + idx] = (double)s.vel[idx];
         g.a[sbase + idx] = (double)s.acc[idx];
-    }
-    __threadfence();  // visible before a progress word is advanced
+    });
+    __threadfence();  // visible device-wide before the flag (raised after the lane's next barrier) can be seen
 }
 
-// Advance the system held in shared memory from step k_begin to k_end (synchronised state in, synchronised
-// state out).  k_begin == 0 additionally handles the initial acceleration and the initial snapshot.
-template <typename T, bool kZeroEps>
-__device__ __forceinline__ void run_steps(const EnsembleArgs& g, int b, int k_begin, int k_end,
-                                          const SystemSmem<T>& s) {
+// Phase F of one lane: this thread's two bodies against its j-part, partial sums into the lane's slab q.
+// kN != 0: the shape is a compile-time constant (kN % shape_parts(kN) == 0), so the j loop has a known trip count.
+template <typename T, bool kZeroEps, int kN>
+__device__ __forceinline__ void force_phase(const EnsembleArgs& g, const SystemSmem<T>& s) {
     using V4 = typename Vec4<T>::type;
-    const int N = g.N, n3 = 3 * N;
+    const int N = kN ? kN : g.N, n3 = 3 * N;
+    const int rows = kN ? shape_rows(kN ? kN : 1) : g.rows;
+    const int parts = kN ? shape_parts(kN ? kN : 1) : g.parts;
     const int tid = threadIdx.x;
-    const int q = tid / g.rows;      // j-part of this thread
-    const int r = tid - q * g.rows;  // row: bodies r and r + rows
-    const bool active = q < g.parts;
-    const int i0 = r, i1 = r + g.rows;
+    const int q = tid / rows;      // j-part of this thread
+    const int r = tid - q * rows;  // row: bodies r and r + rows
+    if (q >= parts) return;
+    const int i0 = r, i1 = r + rows;
     const bool has1 = i1 < N;
-    const int jb = active ? (int)(((long)q * N) / g.parts) : 0;
-    const int je = active ? (int)(((long)(q + 1) * N) / g.parts) : 0;
-    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
-    T* pos_s = reinterpret_cast<T*>(s.pos);
-
-    long pending = -1;  // snapshot row staged but not yet streamed out (uniform across the CTA)
-    for (int k = k_begin; k <= k_end; ++k) {
-        const bool entry_state = (k == k_begin) && (k_begin > 0);  // (x,v,a)_k were finished by the previous chunk
-        const bool do_force = !entry_state && ((k > 0) || g.compute_a0);
-        const bool do_close = !entry_state && k > 0;
-        const bool do_open = k < k_end;
-        long srow = -1;  // get_state() before the loop and every save_interval steps, nbody.py:235,240-241
-        if (g.out_x && !entry_state) {
-            if (k == 0) {
-                if (g.write_initial) srow = g.snap_offset;
-            } else if ((k % g.save_interval) == 0) {
-                srow = g.snap_offset + (g.write_initial ? 1 : 0) + (k / g.save_interval - 1);
-            }
-        }
-        // ---- phase F -----------------------------------------------------------------------------
-        if (pending >= 0) {
-            flush_stage<T>(g, s, b, pending);
-            pending = -1;
-        }
-        if (do_force) {
-            if (active) {
-                const V4 me0 = s.pos[i0];
-                const V4 me1 = s.pos[has1 ? i1 : i0];
-                T ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
+    const int jb = (int)(((long)q * N) / parts);
+    const int je = kN ? jb + kN / shape_parts(kN ? kN : 1) : (int)(((long)(q + 1) * N) / parts);
+    const T eps2 = (T)g.eps2;
+    const V4 me0 = s.pos[i0];
+    const V4 me1 = s.pos[has1 ? i1 : i0];
+    T ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
 #pragma unroll 4
-                for (int j = jb; j < je; ++j) {
-                    const V4 pj = s.pos[j];
-                    pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
-                    pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, eps2, ax1, ay1, az1);
-                }
-                T* pa = s.part + (size_t)q * n3;
-                pa[3 * i0 + 0] = ax0; pa[3 * i0 + 1] = ay0; pa[3 * i0 + 2] = az0;
-                if (has1) { pa[3 * i1 + 0] = ax1; pa[3 * i1 + 1] = ay1; pa[3 * i1 + 2] = az1; }
-            }
-            __syncthreads();
-        }
-        // ---- phase I -----------------------------------------------------------------------------
-        for (int idx = tid; idx < n3; idx += blockDim.x) {
-            const int i = idx / 3, c = idx - 3 * i;
-            T a = s.acc[idx];
-            if (do_force) {
-                a = s.part[idx];
-                for (int p = 1; p < g.parts; ++p) a += s.part[(size_t)p * n3 + idx];
-                s.acc[idx] = a;
-            }
-            T v = s.vel[idx];
-            T x = pos_s[4 * i + c];
-            if (do_close) v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
-            if (srow >= 0) {
-                s.stage[idx] = x;
-                s.stage[n3 + idx] = v;
-                s.stage[2 * n3 + idx] = a;
-            }
-            if (do_open) {
-                v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
-                x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
-                pos_s[4 * i + c] = x;
-            }
-            s.vel[idx] = v;
-        }
-        pending = srow;
-        __syncthreads();
+    for (int j = jb; j < je; ++j) {
+        const V4 pj = s.pos[j];
+        pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
+        pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, eps2, ax1, ay1, az1);
     }
-    if (pending >= 0) flush_stage<T>(g, s, b, pending);
-    __syncthreads();  // stage and state are quiescent for whoever comes next
+    T* pa = s.part + (size_t)q * n3;
+    pa[3 * i0 + 0] = ax0; pa[3 * i0 + 1] = ay0; pa[3 * i0 + 2] = az0;
+    if (has1) { pa[3 * i1 + 0] = ax1; pa[3 * i1 + 1] = ay1; pa[3 * i1 + 2] = az1; }
 }
 
-template <typename T, bool kZeroEps, int kMaxThreads, int kMinBlocks>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ensemble_kernel(const EnsembleArgs g) {
+// Phase I of one lane at step k of piece p: the state becomes (x_k, v_k, a_k), is snapshotted, and (k < p.k1)
+// moves on to the drifted positions of step k + 1.
+template <typename T, int kN>
+__device__ __forceinline__ void integrate_phase(const EnsembleArgs& g, const Piece& p, int k, const SystemSmem<T>& s,
+                                                const Owned& own) {
+    const int N = kN ? kN : g.N, n3 = 3 * N;
+    const int parts = kN ? shape_parts(kN ? kN : 1) : g.parts;
+    const T dt = (T)g.dt, half_dt = (T)g.half_dt;
+    T* pos_s = reinterpret_cast<T*>(s.pos);
+    const bool entry_state = (k == p.k0) && (p.k0 > 0);  // (x,v,a)_k were finished by whoever ran the head
+    const bool do_force = !entry_state && ((k > 0) || g.compute_a0);
+    const bool do_close = !entry_state && k > 0;
+    const bool do_open = k < p.k1;
+    long srow = -1;  // get_state() before the loop and every save_interval steps, nbody.py:235,240-241
+    if (g.out_x && !entry_state) {
+        if (k == 0) {
+            if (g.write_initial) srow = g.snap_offset;
+        } else if ((k % g.save_interval) == 0) {
+            srow = g.snap_offset + (g.write_initial ? 1 : 0) + (k / g.save_interval - 1);
+        }
+    }
+    const size_t orow = srow >= 0 ? ((size_t)p.b * g.n_snap_total + (size_t)srow) * n3 : 0;
+    for_each_owned(own, n3, [&](int idx, int poff) {
+        T a = s.acc[idx];
+        if (do_force) {
+            a = s.part[idx];
+#pragma unroll
+            for (int q = 1; q < 8; ++q)  // parts <= 8; predicated so that every load is in flight before the adds
+                if (q < parts) a += s.part[(size_t)q * n3 + idx];
+            s.acc[idx] = a;
+        }
+        T v = s.vel[idx];
+        T x = pos_s[poff];
+        if (do_close) v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
+        if (srow >= 0) {                                   // get_state(), nbody.py:250-259: coalesced 8-byte stores
+            g.out_x[orow + idx] = (double)x;
+            g.out_v[orow + idx] = (double)v;
+            g.out_a[orow + idx] = (double)a;
+        }
+        if (do_open) {
+            v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
+            x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
+            pos_s[poff] = x;
+        }
+        s.vel[idx] = v;
+    });
+}
+
+constexpr int kMaxLanes = 2;
+constexpr int kForceThreadsMax = 512;                  // rows x parts never exceeds it (shape_parts)
+constexpr int kIntegratorThreads = 128;                // the integrator warps of the two-lane mode
+constexpr int kEnsembleThreadsMax = kForceThreadsMax + kIntegratorThreads;
+
+// kSplit: the two-lane build with integrator warps.  Registers are allocated to warps in groups of four, so a 17th
+// warp costs as much as a 20th: four integrator warps, 20 warps x 96 registers.  The one-lane build keeps 16 warps
+// and up to 128 registers.
+template <typename T, bool kZeroEps, int kN, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? kEnsembleThreadsMax : kForceThreadsMax, 1)
+ensemble_kernel(const EnsembleArgs g) {
     using V4 = typename Vec4<T>::type;
     extern __shared__ __align__(16) char smem[];
-    const int n3 = 3 * g.N;
-    SystemSmem<T> s;
-    s.pos = reinterpret_cast<V4*>(smem);
-    s.vel = reinterpret_cast<T*>(smem + (size_t)g.N * sizeof(V4));
-    s.acc = s.vel + n3;
-    s.part = s.acc + n3;
-    s.stage = s.part + (size_t)g.parts * n3;
-    __shared__ int s_claim;
+    __shared__ __align__(8) uint64_t bar_f[kMaxLanes], bar_i[kMaxLanes];  // "F / I of lane L is done by every warp in it"
+    const int N = kN ? kN : g.N, n3 = 3 * N;
+    const int parts = kN ? shape_parts(kN ? kN : 1) : g.parts;
+    const int lanes = g.lanes;
+    // roles: with an integrator warp the first f_threads only run F and the last warp only runs I
+    const int i_threads = kSplit ? (int)blockDim.x - g.f_threads : 0;
+    const bool split = kSplit;
+    const bool does_f = (int)threadIdx.x < g.f_threads;
+    const bool does_i = !split || !does_f;
+    const Owned own = split ? make_owned(n3, (int)threadIdx.x - g.f_threads, i_threads)
+                            : make_owned(n3, (int)threadIdx.x, (int)blockDim.x);
 
-    // Two CTAs share an SM and would run in lock step: both in the force phase (FP64 pipe saturated), then both
-    // in the integrate phase (pipe idle).  Delaying every second arrival on an SM by about half a step makes
-    // one CTA's integrate phase overlap the other's force phase for the rest of the run.
-    if (g.sm_slots != nullptr && g.stagger_ns > 0) {
-        if (threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            const int arrival = atomicAdd(g.sm_slots + smid, 1);
-            if (arrival & 1) {
-                const long long t0 = clock64();
-                const long long ticks = (long long)g.stagger_ns * 2;  // ~2 GHz SM clock
-                while (clock64() - t0 < ticks) __nanosleep(200);
+    SystemSmem<T> sm[kMaxLanes];
+    Worker wk[kMaxLanes];
+    Piece pc[kMaxLanes];
+    bool active[kMaxLanes];
+    int k[kMaxLanes], publish_b[kMaxLanes];
+    unsigned cyc[kMaxLanes];
+#pragma unroll
+    for (int L = 0; L < kMaxLanes; ++L) {
+        char* base = smem + (size_t)L * lane_smem_bytes<T>(N, parts);
+        sm[L].pos = reinterpret_cast<V4*>(base);
+        sm[L].vel = reinterpret_cast<T*>(base + (size_t)N * sizeof(V4));
+        sm[L].acc = sm[L].vel + n3;
+        sm[L].part = sm[L].acc + n3;
+        active[L] = false;
+        k[L] = 0; publish_b[L] = -1; cyc[L] = 0;
+        if (L < lanes) {
+            wk[L].init((long)blockIdx.x * lanes + L, (long)gridDim.x * lanes, g.B, g.n_steps);
+            active[L] = wk[L].next(pc[L]);
+            if (active[L]) {
+                if (does_i) load_piece<T>(g, pc[L], sm[L], own, N);
+                k[L] = pc[L].k0;
             }
         }
-        __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        const uint32_t f_warps = g.f_threads >> 5, i_warps = (split ? i_threads : (int)blockDim.x) >> 5;
+        for (int L = 0; L < kMaxLanes; ++L) { mbar_init(&bar_f[L], f_warps); mbar_init(&bar_i[L], i_warps); }
+    }
+    __syncthreads();
 
-    // Home systems: CTA c owns systems c, c + grid, ... (whole rounds of the grid) and keeps each one in
-    // shared memory from its first step to its last.  Leftover systems (B mod grid of them) are advanced
-    // chunk by chunk by whichever CTA claims the next (chunk, system) ticket at one of its own chunk
-    // boundaries: it parks its home system in global memory, runs the stolen chunk, and takes its home
-    // system back.  Every CTA steals at most `steal_budget` chunks, which spreads the leftover work evenly.
-    const int grid = gridDim.x;
-    const int home_rounds = g.home_rounds;
-    const int b_home = home_rounds * grid;
-    const int n_left = g.B - b_home;
-    const int n_tickets = n_left * g.n_chunks;
-    const int steal_budget = n_left ? (n_tickets + grid - 1) / grid : 0;
-    int steals = 0;
-
-    // Claim the next leftover ticket if its predecessor chunk is finished (non-blocking unless `block`).
-    auto claim = [&](bool block) -> int {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int got = -1;
-            if (block) {
-                // unconditional draw (atomics pipeline at L2; a CAS loop would serialise 296 CTAs), then wait
-                // for the predecessor chunk: it holds a lower ticket, so some running CTA is executing it
-                const int t = atomicAdd(g.ticket, 1);
-                if (t < n_tickets) {
-                    const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
-                    if (chunk > 0) {
-                        volatile int* flag = g.progress + bl;
-                        while (*flag < chunk) __nanosleep(32);
+    while (active[0] || active[1]) {
+        // ---- F slots ---------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int L = 0; L < kMaxLanes; ++L) {
+            if (!active[L] || !does_f) continue;
+            if (cyc[L] > 0) {  // this lane's previous I slot is complete (and its state parked, if it had to be)
+                mbar_wait_or_trap(&bar_i[L], (cyc[L] - 1) & 1);
+                if (publish_b[L] >= 0 && threadIdx.x == 0) atomicExch(g.progress + publish_b[L], 1);
+            }
+            const bool entry_state = (k[L] == pc[L].k0) && (pc[L].k0 > 0);
+            if (!entry_state && (k[L] > 0 || g.compute_a0)) force_phase<T, kZeroEps, kN>(g, sm[L]);
+            warp_arrive(&bar_f[L]);
+        }
+        // ---- I slots (every thread follows the lanes' bookkeeping; only the integrating threads touch data) --------
+#pragma unroll
+        for (int L = 0; L < kMaxLanes; ++L) {
+            if (!active[L]) continue;
+            if (cyc[L] > 0) publish_b[L] = -1;  // raised by thread 0 in the F slot above
+            if (does_i) {
+                mbar_wait_or_trap(&bar_f[L], cyc[L] & 1);  // every force warp has finished this lane's F slot
+                integrate_phase<T, kN>(g, pc[L], k[L], sm[L], own);
+            }
+            if (k[L] < pc[L].k1) {
+                ++k[L];
+            } else {  // piece finished: park / return the state, take the next piece
+                if (does_i) store_piece<T>(g, pc[L].b, sm[L], own, N);
+                if (pc[L].publish) publish_b[L] = pc[L].b;
+                active[L] = wk[L].next(pc[L]);
+                if (active[L]) {
+                    if (pc[L].wait && (publish_b[0] >= 0 || publish_b[1] >= 0)) {
+                        // The awaited flag may be one this very CTA still has to raise (the other lane's head, in
+                        // runs of a few steps): raise what is pending before anybody polls.
+                        __syncthreads();
+                        if (threadIdx.x == 0)
+                            for (int M = 0; M < kMaxLanes; ++M)
+                                if (publish_b[M] >= 0) atomicExch(g.progress + publish_b[M], 1);
+                        publish_b[0] = publish_b[1] = -1;
                     }
-                    got = t;
-                }
-            } else
-            for (;;) {
-                const int t = *reinterpret_cast<volatile int*>(g.ticket);
-                if (t >= n_tickets) break;
-                const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
-                const bool ready = chunk == 0 || *reinterpret_cast<volatile int*>(g.progress + bl) >= chunk;
-                if (ready) {
-                    if (atomicCAS(g.ticket, t, t + 1) == t) { got = t; break; }
-                } else if (!block) {
-                    break;
-                } else {
-                    __nanosleep(64);
+                    if (does_i) load_piece<T>(g, pc[L], sm[L], own, N);
+                    k[L] = pc[L].k0;
                 }
             }
-            if (got >= 0) __threadfence();
-            s_claim = got;
+            if (does_i) warp_arrive(&bar_i[L]);
+            ++cyc[L];
         }
-        __syncthreads();
-        return s_claim;
-    };
-    auto run_ticket = [&](int t) {
-        const int chunk = t / n_left, bl = b_home + (t - chunk * n_left);
-        const int k0 = chunk * g.chunk_steps, k1 = min(k0 + g.chunk_steps, g.n_steps);
-        load_state<T>(g, bl, s);
-        run_steps<T, kZeroEps>(g, bl, k0, k1, s);
-        store_state<T>(g, bl, s);
-        __syncthreads();
-        if (threadIdx.x == 0) atomicExch(g.progress + bl, chunk + 1);
-    };
-
-    // Home boundaries (where a CTA may steal) are every kPeekSteps steps, staggered by CTA so that at every
-    // step some CTAs are at a boundary and a leftover chunk is picked up as soon as it becomes ready.
-    constexpr int kPeekSteps = 8;
-    const int phase = blockIdx.x % kPeekSteps;
-    for (int round = 0; round < home_rounds; ++round) {
-        const int b = blockIdx.x + round * grid;
-        load_state<T>(g, b, s);
-        int k0 = 0;
-        do {
-            int k1 = g.n_steps;
-            if (n_tickets && steals < steal_budget) {
-                const int d = ((k0 - phase) % kPeekSteps + kPeekSteps) % kPeekSteps;
-                k1 = min(k0 + (kPeekSteps - d), g.n_steps);
-            }
-            run_steps<T, kZeroEps>(g, b, k0, k1, s);
-            const bool last = k1 >= g.n_steps;
-            if (last) store_state<T>(g, b, s);
-            if (n_tickets && steals < steal_budget) {
-                const int t = claim(false);
-                if (t >= 0) {
-                    if (!last) store_state<T>(g, b, s);
-                    run_ticket(t);
-                    ++steals;
-                    if (!last) load_state<T>(g, b, s);
-                }
-            }
-            k0 = k1;
-        } while (k0 < g.n_steps);
     }
-    // whatever leftover work is still unclaimed (short runs with a single chunk, or no home round at all)
-    while (n_tickets) {
-        const int t = claim(true);
-        if (t < 0) break;
-        run_ticket(t);
-    }
+    // a head is always followed by other pieces of the same worker, so no flag is pending here; be safe anyway
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int L = 0; L < kMaxLanes; ++L)
+            if (publish_b[L] >= 0) atomicExch(g.progress + publish_b[L], 1);
 }
 
 constexpr int kEnsembleMaxBodies = 1024;
@@ -391,63 +473,43 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     g.n_steps = n_steps; g.save_interval = save_interval; g.compute_a0 = compute_a0; g.write_initial = write_initial;
     g.out_x = out_x; g.out_v = out_v; g.out_a = out_a;
     g.n_snap_total = n_snap_total; g.snap_offset = snap_offset;
-    // two bodies per thread; as many j-parts as fit in 512 threads (at most 8)
-    g.rows = ceil_div(N, 2);
-    int parts = 512 / g.rows;
-    if (parts < 1) parts = 1;
-    if (parts > 8) parts = 8;
-    if (parts > N) parts = N;
+    g.rows = shape_rows(N);
+    const int parts = shape_parts(N);
     g.parts = parts;
-    const int threads = round_up(g.rows * parts, 32);
-    const size_t smem = ensemble_smem_bytes<T>(N, parts);
+    static_assert(200 % shape_parts(200) == 0, "the static N=200 shape needs equal j-parts");
+    g.f_threads = round_up(g.rows * parts, 32);
     const bool zero = !((T)g.eps2 > T(0));
-    // up to 512 threads: two CTAs per SM on a 64-register budget; more rows: one CTA per SM
-    void (*kern)(const EnsembleArgs);
-    if (threads <= 512 && 2 * smem <= 200 * 1024)
-        kern = zero ? ensemble_kernel<T, true, 512, 2> : ensemble_kernel<T, false, 512, 2>;
-    else
-        kern = zero ? ensemble_kernel<T, true, 1024, 1> : ensemble_kernel<T, false, 1024, 1>;
-    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, dev = 0, sms = 0;
+    int dev = 0, sms = 0, smem_max = 0;
     NB_CUDA_OK(cudaGetDevice(&dev));
     NB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NB_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // Two lanes + the integrator warp when there are systems for 2 x SMs workers and both lanes fit in shared
+    // memory; else one lane, every thread in both phases.
+    const size_t lane_bytes = lane_smem_bytes<T>(N, parts);
+    g.lanes = (B >= 2 * sms && 2 * lane_bytes + 1024 <= (size_t)smem_max) ? 2 : 1;
+    const int threads = g.f_threads + (g.lanes == 2 ? kIntegratorThreads : 0);
+    const size_t smem = (size_t)g.lanes * lane_bytes;
+    void (*kern)(const EnsembleArgs);
+    const bool split = g.lanes == 2;
+    if (N == 200 && !zero)  // the reference's data-generation shape (generate_data.py:109), compiled with constant bounds
+        kern = split ? ensemble_kernel<T, false, 200, true> : ensemble_kernel<T, false, 200, false>;
+    else if (split)
+        kern = zero ? ensemble_kernel<T, true, 0, true> : ensemble_kernel<T, false, 0, true>;
+    else
+        kern = zero ? ensemble_kernel<T, true, 0, false> : ensemble_kernel<T, false, 0, false>;
+    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
     NB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     NB_REQUIRE(per_sm >= 1, "ensemble kernel does not fit on an SM (N=%d threads=%d smem=%zu)", N, threads, smem);
-    const int resident = per_sm * sms;
-    const int grid = B < resident ? B : resident;
-    // Leftover systems (B mod grid) advance in chunks of 20 steps, each chunk stolen by a home CTA.
-    g.ticket = nullptr; g.progress = nullptr; g.chunk_steps = n_steps > 0 ? n_steps : 1; g.n_chunks = 1;
-    g.home_rounds = B / grid;
-    g.sm_slots = nullptr; g.stagger_ns = 0;
-    if (per_sm >= 2 && ws && ws_bytes >= nb_ensemble_workspace_bytes(B)) {
-        // half of one shared step: N^2 interactions x 16 FP64 ops on a 64-lane pipe at ~1.9 GHz
-        const double step_ns = (double)N * N * 16.0 / (64.0 * 1.9);
-        g.stagger_ns = (unsigned)(step_ns > 4.0e6 ? 4.0e6 : step_ns);
-        g.sm_slots = static_cast<int*>(ws) + (size_t)B + 1;
-        NB_CUDA_OK(cudaMemsetAsync(g.sm_slots, 0, sizeof(int) * 1024, st));
-    }
-    if (B % grid != 0) {
+    // persistent grid, one CTA per SM; with fewer systems than SMs, one system per CTA
+    const int grid = B < sms ? B : sms;
+    // A system is shared by two workers whenever the B x n_steps line does not divide evenly: per-system flags
+    g.progress = nullptr;
+    if (B % (grid * g.lanes) != 0) {
         NB_REQUIRE(ws && ws_bytes >= nb_ensemble_workspace_bytes(B), "ensemble workspace too small: %zu < %zu",
                    ws_bytes, nb_ensemble_workspace_bytes(B));
-        if (B % grid <= grid / 8) {
-            // a few leftover systems: 20-step chunks stolen by the home CTAs
-            if (n_steps >= 40) {
-                g.chunk_steps = 20;
-                g.n_chunks = ceil_div(n_steps, 20);
-            }
-        } else {
-            // many: no home systems, every system advances by tickets (~48 per CTA, chunks of >= 8 steps)
-            g.home_rounds = 0;
-            int steps = ceil_div(n_steps, ceil_div(48 * grid, B));
-            if (steps < 8) steps = 8;
-            if (n_steps >= 16) {
-                g.chunk_steps = steps;
-                g.n_chunks = ceil_div(n_steps, steps);
-            }
-        }
-        g.ticket = static_cast<int*>(ws);
-        g.progress = g.ticket + 1;
-        NB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(int) * ((size_t)B + 1), st));
+        g.progress = static_cast<int*>(ws);
+        NB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)B, st));
     }
     kern<<<grid, threads, smem, st>>>(g);
     return check_launch("ensemble kernel");
@@ -459,8 +521,8 @@ extern "C" {
 
 int nb_ensemble_max_bodies(void) { return nb::kEnsembleMaxBodies; }
 
-// ticket counter + per-system progress words + per-SM arrival counters
-size_t nb_ensemble_workspace_bytes(int B) { return (sizeof(int) * ((size_t)(B > 0 ? B : 0) + 1 + 1024) + 255) / 256 * 256; }
+// per-system hand-over flags
+size_t nb_ensemble_workspace_bytes(int B) { return (sizeof(int) * ((size_t)(B > 0 ? B : 0) + 1) + 255) / 256 * 256; }
 
 int nb_ensemble_f64(double* x, double* v, double* a, const void* masses, int masses_are_f32, int mass_stride, int B,
                     int N, double dt, double softening, int n_steps, int save_interval, int compute_a0,

@@ -94,9 +94,10 @@ def test_ensemble_vs_golden_and_oracle(golden, oracle_mod):
     assert np.array_equal(out["times"], chk["times"])
 
 
-def test_ensemble_ticket_mode_matches_static(engine):
-    """More systems than resident CTAs switches K3 to the chunked ticket scheduler; the result must
-    be bit-identical to running the same systems in small static batches."""
+def test_ensemble_interval_schedule_matches_small_batches(engine):
+    """More systems than workers: K3 cuts the systems x steps line into one interval per worker, so systems are
+    handed from one CTA lane to the next in mid-run; the result must be bit-identical to running the same
+    systems in small batches (one system per CTA, no hand-over)."""
     from hpc import ics
     from hpc.ensemble import simulate_ensemble
     B = 3 * engine.sm_count * 2 + 5
@@ -314,8 +315,8 @@ def test_ensemble_body_counts(oracle_mod, n):
 
 
 def test_ensemble_f32_and_leftover_scheduler(engine):
-    """float32 ensemble within 1e-5 of float64; B slightly above the resident grid (home + stolen chunks) and
-    far above it (all tickets) give the same bits as small static batches, with per-system masses."""
+    """float32 ensemble within 1e-5 of float64; B slightly above the worker count (two lanes per SM) and far
+    above it give the same bits as small batches, with per-system masses."""
     from hpc.ensemble import simulate_ensemble
     rng = np.random.RandomState(5)
     grid = 2 * engine.sm_count
@@ -332,3 +333,25 @@ def test_ensemble_f32_and_leftover_scheduler(engine):
     f32 = simulate_ensemble(x0[:8], v0[:8], m[:8], dt=1e-3, softening=0.05, n_steps=60, save_interval=5, dtype="float32")
     f64 = simulate_ensemble(x0[:8], v0[:8], m[:8], dt=1e-3, softening=0.05, n_steps=60, save_interval=5)
     assert np.abs(f32["positions"] - f64["positions"]).max() / np.abs(f64["positions"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("n_steps", [0, 1, 2, 3, 7])
+def test_ensemble_short_runs_hand_over(engine, n_steps):
+    """Runs of a few steps with systems shared between workers: heads of one or two steps, a tail that waits for
+    a flag raised by the other lane of the same CTA, the n_steps == 0 launch (a_0 and the first snapshot only).
+    B is chosen so that the systems x steps line does not divide by the worker count."""
+    from hpc.ensemble import simulate_ensemble
+    rng = np.random.RandomState(11 + n_steps)
+    workers = 2 * engine.sm_count
+    for B in (workers + 1, workers + workers // 2 + 1, engine.sm_count + 3):
+        x0 = rng.rand(B, 24, 3) * 4 - 2
+        v0 = rng.rand(B, 24, 3) - 0.5
+        m = rng.uniform(1e9, 1e10, 24)
+        big = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, n_steps=n_steps, save_interval=1)
+        assert big["positions"].shape == (B, n_steps + 1, 24, 3)
+        for lo in (0, B // 2, B - 40):
+            small = simulate_ensemble(x0[lo:lo + 40], v0[lo:lo + 40], m, dt=1e-3, softening=0.05, n_steps=n_steps,
+                                      save_interval=1)
+            for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities",
+                        "final_accelerations"):
+                assert np.array_equal(big[key][lo:lo + 40], small[key]), (B, lo, key)

@@ -64,10 +64,43 @@ __device__ __forceinline__ void pair_seed(double xi, double yi, double zi, doubl
     ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
 }
 
+
+// ---- stage-wise interleaving: kC independent interactions written stage by stage, so that ptxas keeps kC chains in
+// flight instead of finishing one interaction before starting the next ----
+template <int kC>
+__device__ __forceinline__ void pairs_staged(const double (&xi)[kC], const double (&yi)[kC], const double (&zi)[kC],
+                                             const double (&xj)[kC], const double (&yj)[kC], const double (&zj)[kC],
+                                             const double (&gm)[kC], double eps2, double* (&ax)[kC], double* (&ay)[kC],
+                                             double* (&az)[kC]) {
+    double dx[kC], dy[kC], dz[kC], r2[kC], y0[kC], y2[kC], e[kC], g[kC], w[kC], p[kC], q[kC], f[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { dx[c] = xj[c] - xi[c]; dy[c] = yj[c] - yi[c]; dz[c] = zj[c] - zi[c]; }
+#pragma unroll
+    for (int c = 0; c < kC; ++c) r2[c] = fma(dx[c], dx[c], eps2);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) r2[c] = fma(dy[c], dy[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) r2[c] = fma(dz[c], dz[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) y0[c] = rsqrt_seed(r2[c]);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { y2[c] = y0[c] * y0[c]; g[c] = gm[c] * y0[c]; }
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { e[c] = fma(-r2[c], y2[c], 1.0); w[c] = y2[c] * g[c]; }
+#pragma unroll
+    for (int c = 0; c < kC; ++c) p[c] = fma(1.875, e[c], 1.5);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) q[c] = e[c] * p[c];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) f[c] = fma(w[c], q[c], w[c]);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { *ax[c] = fma(f[c], dx[c], *ax[c]); *ay[c] = fma(f[c], dy[c], *ay[c]); *az[c] = fma(f[c], dz[c], *az[c]); }
+}
+
 // kN bodies, kRows x kParts force threads (two bodies per thread), kThreads per CTA.
 // kDirect: snapshot rows are stored from the integrate phase straight to HBM (no shared stage, no flush pass).
 // kRegs:   velocity / acceleration scalars live in registers of their owner thread.
-template <int kN, int kRows, int kParts, int kThreads, int kMinBlocks, bool kDirect, bool kRegs, bool kTrace, int kUnroll, int kBPT, bool kForceOnly, int kSeed = 0>
+template <int kN, int kRows, int kParts, int kThreads, int kMinBlocks, bool kDirect, bool kRegs, bool kTrace, int kUnroll, int kBPT, bool kForceOnly, int kSeed = 0, int kInter = 0>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) ens_v1(const Args g) {
     constexpr int n3 = 3 * kN;
     constexpr int kE = (n3 + kThreads - 1) / kThreads;  // integrator scalars per thread
@@ -156,12 +189,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) ens_v1(const Args g) {
                     mx[m] = me.x; my[m] = me.y; mz[m] = me.z;
                     ax[m] = ay[m] = az[m] = 0.0;
                 }
+                if (kInter == 2 && kBPT == 2) {
+#pragma unroll kUnroll
+                    for (int j = jb; j < je; ++j) {
+                        const double4 pj = pos[j];
+                        const double xi_[2] = {mx[0], mx[1]}, yi_[2] = {my[0], my[1]}, zi_[2] = {mz[0], mz[1]};
+                        const double xj_[2] = {pj.x, pj.x}, yj_[2] = {pj.y, pj.y}, zj_[2] = {pj.z, pj.z}, gm_[2] = {pj.w, pj.w};
+                        double* axp[2] = {&ax[0], &ax[1]}; double* ayp[2] = {&ay[0], &ay[1]}; double* azp[2] = {&az[0], &az[1]};
+                        pairs_staged<2>(xi_, yi_, zi_, xj_, yj_, zj_, gm_, eps2, axp, ayp, azp);
+                    }
+                } else if (kInter == 4 && kBPT == 2) {
+#pragma unroll kUnroll
+                    for (int j = jb; j < je; j += 2) {
+                        const double4 pa = pos[j], pb = pos[j + 1];
+                        const double xi_[4] = {mx[0], mx[1], mx[0], mx[1]}, yi_[4] = {my[0], my[1], my[0], my[1]}, zi_[4] = {mz[0], mz[1], mz[0], mz[1]};
+                        const double xj_[4] = {pa.x, pa.x, pb.x, pb.x}, yj_[4] = {pa.y, pa.y, pb.y, pb.y}, zj_[4] = {pa.z, pa.z, pb.z, pb.z}, gm_[4] = {pa.w, pa.w, pb.w, pb.w};
+                        double* axp[4] = {&ax[0], &ax[1], &ax[0], &ax[1]}; double* ayp[4] = {&ay[0], &ay[1], &ay[0], &ay[1]}; double* azp[4] = {&az[0], &az[1], &az[0], &az[1]};
+                        // chains 0/2 and 1/3 share accumulators: add the pair (0,1) first, then (2,3)
+                        double* a01x[2] = {axp[0], axp[1]}; (void)a01x;
+                        pairs_staged<4>(xi_, yi_, zi_, xj_, yj_, zj_, gm_, eps2, axp, ayp, azp);
+                    }
+                } else {
 #pragma unroll kUnroll
                 for (int j = jb; j < je; ++j) {
                     const double4 pj = pos[j];
 #pragma unroll
                     for (int m = 0; m < kBPT; ++m)
                         pair_seed<kSeed>(mx[m], my[m], mz[m], pj.x, pj.y, pj.z, pj.w, eps2, ax[m], ay[m], az[m]);
+                }
                 }
                 double* pa = part + q * n3;
 #pragma unroll
@@ -474,7 +529,7 @@ static bool same(Host& h, const char* what) {
     return ok;
 }
 
-template <int kN, int kRows, int kParts, int kThreads, int kMinBlocks, bool kDirect, bool kRegs, int kUnroll, int kBPT = 2, bool kForceOnly = false, int kSeed = 0>
+template <int kN, int kRows, int kParts, int kThreads, int kMinBlocks, bool kDirect, bool kRegs, int kUnroll, int kBPT = 2, bool kForceOnly = false, int kSeed = 0, int kInter = 0>
 static void run_variant(Host& h, const char* name, bool stagger, bool trace) {
     constexpr int n3 = 3 * kN;
     const size_t smem = (size_t)kN * 32 + (size_t)(kParts + 2 + 3) * n3 * 8;
@@ -485,8 +540,8 @@ static void run_variant(Host& h, const char* name, bool stagger, bool trace) {
     g.sm_slots = stagger ? h.slots : nullptr;
     g.stagger_ns = (unsigned)((double)kN * kN * 16.0 / (64.0 * 1.9));
     g.trace = h.trace;
-    auto kern = ens_v1<kN, kRows, kParts, kThreads, kMinBlocks, kDirect, kRegs, false, kUnroll, kBPT, kForceOnly, kSeed>;
-    auto kern_t = ens_v1<kN, kRows, kParts, kThreads, kMinBlocks, kDirect, kRegs, true, kUnroll, kBPT, kForceOnly, kSeed>;
+    auto kern = ens_v1<kN, kRows, kParts, kThreads, kMinBlocks, kDirect, kRegs, false, kUnroll, kBPT, kForceOnly, kSeed, kInter>;
+    auto kern_t = ens_v1<kN, kRows, kParts, kThreads, kMinBlocks, kDirect, kRegs, true, kUnroll, kBPT, kForceOnly, kSeed, kInter>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -608,7 +663,16 @@ int main(int argc, char** argv) {
     });
     printf("\n");
 
-    run_variant<200, 100, 5, 512, 2, true, false, 4>(h, "direct, 2 bodies x 5 parts, 2 CTA/SM", false, true);
-    run_variant<200, 100, 5, 512, 1, true, true, 4>(h, "direct, 2 bodies x 5 parts, 1 CTA/SM", false, true);
+    printf("---- force phase only, 1 CTA/SM (16 warps) ----\n");
+    run_variant<200, 100, 5, 512, 1, true, true, 4, 2, true, 0, 0>(h, "F-only 1 CTA/SM, compiler order, unroll 4", false, false);
+    run_variant<200, 100, 5, 512, 1, true, true, 4, 2, true, 0, 2>(h, "F-only 1 CTA/SM, 2 chains staged, unroll 4", false, false);
+    run_variant<200, 100, 5, 512, 1, true, true, 2, 2, true, 0, 2>(h, "F-only 1 CTA/SM, 2 chains staged, unroll 2", false, false);
+    run_variant<200, 100, 5, 512, 1, true, true, 1, 2, true, 0, 2>(h, "F-only 1 CTA/SM, 2 chains staged, unroll 1", false, false);
+    run_variant<200, 100, 5, 512, 1, true, true, 2, 2, true, 0, 4>(h, "F-only 1 CTA/SM, 4 chains staged, unroll 2", false, false);
+    run_variant<200, 100, 5, 512, 1, true, true, 1, 2, true, 0, 4>(h, "F-only 1 CTA/SM, 4 chains staged, unroll 1", false, false);
+    printf("---- force phase only, 2 CTA/SM (32 warps, 64 regs) ----\n");
+    run_variant<200, 100, 5, 512, 2, true, true, 4, 2, true, 0, 0>(h, "F-only 2 CTA/SM, compiler order, unroll 4", false, false);
+    run_variant<200, 100, 5, 512, 2, true, true, 2, 2, true, 0, 2>(h, "F-only 2 CTA/SM, 2 chains staged, unroll 2", false, false);
+    run_variant<200, 100, 5, 512, 2, true, true, 1, 2, true, 0, 4>(h, "F-only 2 CTA/SM, 4 chains staged, unroll 1", false, false);
     return 0;
 }
