@@ -244,7 +244,7 @@ class Engine:
         acc = torch.empty((n_i, 3), dtype=stream.dtype, device=self.device)
         self._check(getattr(self.lib, f"nb_accel_{sfx}")(self._p(stream), n, i0, n_i, float(softening), self._p(acc),
                                                           self._p(ws[0]), ws[1], self._stream()))
-        self.launches += 2
+        self.launches += 1  # the force kernel reduces its own segment partials
         return acc
 
     def kick_drift_slab(self, cur, nxt, vel, acc, n: int, i0: int, n_i: int, dt: float):
@@ -262,7 +262,7 @@ class Engine:
             self._p(cur), self._p(nxt), self._p(vel), self._p(acc), n, i0, n_i, float(dt), float(softening),
             int(flags), self._p(snap_pos), self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1],
             self._stream()))
-        self.launches += 2
+        self.launches += 1  # force, segment reduction and leapfrog are one kernel
 
     def step_peer_slab(self, cur, next_ptrs, flag_ptrs, my_rank: int, wait_seq: int, signal_seq: int, vel, acc,
                        n: int, i0: int, n_i: int, dt: float, softening: float, flags: int, snap_pos, snap_vel,
@@ -278,7 +278,7 @@ class Engine:
             self._p(cur), nxt, flg, P, int(my_rank), int(wait_seq) & 0xFFFFFFFF, int(signal_seq) & 0xFFFFFFFF,
             self._p(vel), self._p(acc), n, i0, n_i, float(dt), float(softening), int(flags), self._p(snap_pos),
             self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1], self._stream()))
-        self.launches += 2
+        self.launches += 1  # force + leapfrog + peer stores + arrival words: one kernel
 
     # ---- host-level operations (ndarrays in, ndarrays out; the reference's call shapes) ----------
     def accelerations(self, positions, masses, softening: float, dtype=np.float64) -> np.ndarray:
@@ -330,18 +330,28 @@ class Engine:
                 sc = torch.empty_like(sp)
             else:
                 sp = sv = sc = None
-            fin = ctypes.c_int(1)
-            self._check(getattr(self.lib, f"nb_run_{sfx}")(
-                self._p(sa), self._p(sb), self._p(vel), self._p(acc), n, float(dt), float(softening), int(n_steps),
-                int(save_interval), self._p(sp), self._p(sv), self._p(sc), self._p(ws[0]), ws[1], fin,
-                self._stream()))
-            self.launches += (1 if snapshots else 0) + (1 if n_steps else 0) + 2 * n_steps
-            final_pos = self.unpack(sa if fin.value else sb, n)
+            in_a = self.run_device(sa, sb, vel, acc, n, dt, softening, n_steps, save_interval, sp, sv, sc, ws)
+            final_pos = self.unpack(sa if in_a else sb, n)
             res = {"final_positions": self.to_host(final_pos), "final_velocities": self.to_host(vel),
                    "final_accelerations": self.to_host(acc)}
             if snapshots:
                 res.update(positions=self.to_host(sp), velocities=self.to_host(sv), accelerations=self.to_host(sc))
             return res
+
+    def run_device(self, stream_a, stream_b, vel, acc, n: int, dt: float, softening: float, n_steps: int,
+                   save_interval: int, snap_pos, snap_vel, snap_acc, ws) -> bool:
+        """The whole step loop of one system on device tensors, enqueued by ONE C call (nb_run_*): opening
+        kick + drift, then one fused force + leapfrog launch per step.  Returns True when the final positions
+        are in stream_a."""
+        torch = _torch()
+        sfx = "f64" if stream_a.dtype == torch.float64 else "f32"
+        fin = ctypes.c_int(1)
+        self._check(getattr(self.lib, f"nb_run_{sfx}")(
+            self._p(stream_a), self._p(stream_b), self._p(vel), self._p(acc), n, float(dt), float(softening),
+            int(n_steps), int(save_interval), self._p(snap_pos), self._p(snap_vel), self._p(snap_acc),
+            self._p(ws[0]), ws[1], fin, self._stream()))
+        self.launches += (1 if snap_pos is not None else 0) + (1 if n_steps else 0) + n_steps
+        return bool(fin.value)
 
     def ensemble_device(self, x, v, a, m_d, masses_f32: int, mass_stride: int, B: int, N: int, dt: float,
                         softening: float, n_steps: int, save_interval: int, dtype, compute_a0: bool,

@@ -132,6 +132,14 @@ class ShardedSystem:
         if n_steps <= 0:
             return
         eng = self.eng
+        if self.world == 1:
+            # one GPU: the whole loop is enqueued by one C call (no per-step Python between launches)
+            in_a = eng.run_device(self.cur, self.nxt, self.vel, self.acc, self.n, self.dt, self.softening, n_steps,
+                                  save_interval, snap_pos, snap_vel, snap_acc, self.ws)
+            if not in_a:
+                self.cur, self.nxt = self.nxt, self.cur
+            self.steps_done += n_steps
+            return
         if self.n_i:
             eng.kick_drift_slab(self.cur, self.nxt, self.vel, self.acc, self.n, self.i0, self.n_i, self.dt)
         self._exchange(self.nxt)
