@@ -165,7 +165,8 @@ int nb_run_f32(float* stream_a, float* stream_b, float* vel, float* acc, int n, 
  * N is limited by shared memory (nb_ensemble_max_bodies()).  f32 variant computes forces and
  * integrates in float32 and converts on the way in and out. */
 int nb_ensemble_max_bodies(void);
-/* Device scratch for the ticket scheduler (zeroed by the call itself). */
+/* Device scratch: one hand-over flag per system, for systems whose steps are shared by two neighbouring workers
+ * of the interval schedule (zeroed by the call itself). */
 size_t nb_ensemble_workspace_bytes(int B);
 int nb_ensemble_f64(double* x, double* v, double* a, const void* masses, int masses_are_f32, int mass_stride,
                     int B, int N, double dt, double softening, int n_steps, int save_interval,

@@ -355,3 +355,26 @@ def test_ensemble_short_runs_hand_over(engine, n_steps):
             for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities",
                         "final_accelerations"):
                 assert np.array_equal(big[key][lo:lo + 40], small[key]), (B, lo, key)
+
+
+def test_ensemble_two_lanes_float32_and_n200(engine, oracle_mod):
+    """The two-lane build (integrator warps; B >= 2 x SMs) in float32 and at the compile-time N = 200 shape:
+    float64 rows equal the oracle, float32 within 1e-5, and both equal their own one-lane runs bit for bit."""
+    from hpc import ics
+    from hpc.ensemble import simulate_ensemble
+    B = 2 * engine.sm_count + 7
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=321)
+    kw = dict(dt=1e-3, softening=0.05, n_steps=12, save_interval=3)
+    out64 = simulate_ensemble(x0, v0, m32, **kw)
+    out32 = simulate_ensemble(x0, v0, m32, dtype="float32", **kw)
+    for b in (0, B // 2, B - 1):
+        chk = oracle_mod.run(x0[b], v0[b], oracle_mod.accel_direct(x0[b], m32, 0.05), m32, 1e-3, 0.05, 12, 3)
+        assert np.abs(out64["positions"][b] - chk["positions"]).max() < POS_TOL
+        assert np.abs(out64["velocities"][b] - chk["velocities"]).max() < 1e-8 * max(1.0, np.abs(chk["velocities"]).max())
+        scale = np.abs(chk["positions"]).max()
+        assert np.abs(out32["positions"][b] - chk["positions"]).max() / scale < 1e-5
+    for out, dtype in ((out64, "float64"), (out32, "float32")):
+        for lo in (0, B - 30):
+            small = simulate_ensemble(x0[lo:lo + 30], v0[lo:lo + 30], m32, dtype=dtype, **kw)   # one lane, 30 CTAs
+            for key in ("positions", "velocities", "accelerations", "final_positions"):
+                assert np.array_equal(out[key][lo:lo + 30], small[key]), (dtype, lo, key)
