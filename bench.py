@@ -311,6 +311,8 @@ def bench_ensemble(args, world, rank, local):
         cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_sims} of {B} simulations x {N} bodies x {T} steps, one thread per simulation, {s_cpu:.1f} s"}
     extra = single_system_extras(eng) if (rank == 0 and not args.no_extras) else None
+    if extra is not None:
+        extra["window_gather_300x401x200_L10"] = window_extras(eng, outs[0][0], outs[0][1])
     return {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 4), "higher_is_better": True,
@@ -327,6 +329,38 @@ def bench_ensemble(args, world, rank, local):
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
         "also": extra,
     }
+
+
+def window_extras(eng, pos_d, vel_d) -> dict:
+    """K5: the (input sequence, next state) samples of the ensemble's trajectories, from the snapshot
+    stacks the timed kernel just wrote.  HBM-bound: 24*N bytes read per state, 24*N*(L+1) written per sample."""
+    import torch
+    B, rows, N = int(pos_d.shape[0]), int(pos_d.shape[1]), int(pos_d.shape[2])
+    L, stride = 10, 1                                  # generate_data.py:172, checkpoint.py:304-305 defaults
+    ins, tgs = eng.window_gather(pos_d, vel_d, rows, L, stride)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        eng.lib.nb_window_gather_f32(eng._p(pos_d), eng._p(vel_d), B, rows, N, rows, L, stride, eng._p(ins),
+                                     eng._p(tgs), eng._stream())
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # context: a plain device fill of the same output volume (library kernel, write-only stream)
+    e0.record()
+    ins.zero_()
+    tgs.zero_()
+    e1.record()
+    e1.synchronize()
+    fill_gbs = (ins.numel() + tgs.numel()) * 4 / e0.elapsed_time(e1) / 1e6
+    bytes_alg = 2.0 * pos_d.numel() * 8 + ins.numel() * 4 + tgs.numel() * 4
+    peaks = measured_peaks()
+    gbs = bytes_alg / ms / 1e6
+    return {"ms": round(ms, 4), "samples": int(ins.shape[0]), "algorithmic_bytes": bytes_alg,
+            "achieved_GBps": round(gbs, 1), "hbm_peak_GBps": peaks["hbm_gbs"], "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+            "device_fill_of_the_outputs_GBps": round(fill_gbs, 1), "l2": "6.2 GB written per launch (>> 126 MB L2)"}
 
 
 def single_system_extras(eng) -> dict:

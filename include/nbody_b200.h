@@ -194,6 +194,18 @@ int nb_energy_f64(const double* pos, const double* vel, const void* masses, int 
                   int n, int i0, int n_i, double softening, double* out_ku,
                   void* workspace, size_t workspace_bytes, nb_stream_t s);
 
+/* ---- K5: sliding-window training samples --------------------------------------------------------
+ * Replaces the sample loop of create_training_dataset, reference src/hpc/checkpoint.py:362-384
+ * (and the sample count of :333): for every trajectory b of an ensemble whose float64 snapshot stacks
+ * pos, vel (B, rows, N, 3) are in device memory, and every start i in range(0, n_states - L, stride),
+ *   inputs [b*S + s] = concat(pos[b, i:i+L], vel[b, i:i+L], axis=-1) as float32   (L, N, 6)
+ *   targets[b*S + s] = concat(pos[b, i+L],   vel[b, i+L],   axis=-1) as float32   (N, 6)
+ * with S = nb_window_count(n_states, L, stride) samples per trajectory; n_states <= rows is the
+ * trajectory's 'n_steps' entry (the number of stored states, generate_data.py:57). */
+int nb_window_count(int n_states, int sequence_length, int stride);
+int nb_window_gather_f32(const double* pos, const double* vel, int B, int rows, int N, int n_states,
+                         int sequence_length, int stride, float* inputs, float* targets, nb_stream_t s);
+
 /* ---- host-buffer entry points ---------------------------------------------------------------------
  * The same operations for callers that hold host arrays and no CUDA state (what a cgo/JNI/ctypes
  * binder of a host-language port would call).  Synchronous. */

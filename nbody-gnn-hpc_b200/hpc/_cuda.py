@@ -68,6 +68,8 @@ _SIGNATURES = {
     "nb_copy_rows_d2h_async": (_ci, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "nb_energy_workspace_bytes": (_sz, [_ci, _ci]),
     "nb_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
+    "nb_window_count": (_ci, [_ci, _ci, _ci]),
+    "nb_window_gather_f32": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp]),
     "nbh_accel_direct": (_ci, [_vp, _vp, _ci, _ci, _cd, _ci, _vp]),
     "nbh_run": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _vp, _vp, _vp]),
     "nbh_ensemble_run": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _vp, _vp, _vp]),
@@ -370,7 +372,7 @@ class Engine:
         self.launches += 1
 
     def ensemble(self, x0, v0, masses, dt: float, softening: float, n_steps: int, save_interval: int = 1,
-                 dtype=np.float64, a0=None, snapshots: bool = True) -> dict:
+                 dtype=np.float64, a0=None, snapshots: bool = True, outputs: str = "host") -> dict:
         """B independent systems (reference generate_data.py:32-58,142-149): host arrays in and out.
 
         x0, v0: (B,N,3); masses: (N,) shared or (B,N).  a0 None -> evaluated from x0 (what the
@@ -411,6 +413,15 @@ class Engine:
                                      out_a=None, n_snap_total=0, snap_offset=0)
                 return {"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
                         "final_accelerations": self.to_host(a)}
+            if outputs == "device":
+                # the stacks stay in HBM: one launch, nothing crosses PCIe but the final state
+                ox = torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=self.device)
+                ov, oa = torch.empty_like(ox), torch.empty_like(ox)
+                self.ensemble_device(x, v, a, m_d, f32, mass_stride, B, N, dt, softening, n_steps, save_interval,
+                                     dtype, compute_a0=a0 is None, write_initial=True, out_x=ox, out_v=ov, out_a=oa,
+                                     n_snap_total=n_snap, snap_offset=0)
+                return {"positions": ox, "velocities": ov, "accelerations": oa, "final_positions": self.to_host(x),
+                        "final_velocities": self.to_host(v), "final_accelerations": self.to_host(a)}
             host = [torch.empty((B, n_snap, N, 3), dtype=torch.float64, pin_memory=True) for _ in range(3)]
             # (Letting the kernel store its rows straight into the pinned host arrays through UVA was measured
             # too: 35.4 ms per 300x200x400 ensemble against 34.6 ms for the staged, chunked copy below.)
@@ -475,6 +486,24 @@ class Engine:
             ku = self.energy_slab(pos_d, vel_d, m_d, f32, n, 0, n, softening)
             k, u = (float(t) for t in ku.cpu())
         return k, u, k + u
+
+    def window_gather(self, pos_d, vel_d, n_states: int, sequence_length: int, stride: int = 1):
+        """K5 on device snapshot stacks (B, rows, N, 3) float64: (inputs (B*S, L, N, 6), targets (B*S, N, 6)) float32
+        device tensors, trajectory-major -- the sample loop of reference checkpoint.py:362-384 for B trajectories."""
+        torch = _torch()
+        B, rows, N = int(pos_d.shape[0]), int(pos_d.shape[1]), int(pos_d.shape[2])
+        if not (pos_d.is_contiguous() and vel_d.is_contiguous() and pos_d.dtype == torch.float64
+                and vel_d.dtype == torch.float64 and tuple(vel_d.shape) == tuple(pos_d.shape) and pos_d.shape[3] == 3):
+            raise ValueError("window_gather needs contiguous float64 (B, rows, N, 3) position and velocity stacks")
+        S = int(self.lib.nb_window_count(int(n_states), int(sequence_length), int(stride)))
+        inputs = torch.empty((B * S, sequence_length, N, 6), dtype=torch.float32, device=self.device)
+        targets = torch.empty((B * S, N, 6), dtype=torch.float32, device=self.device)
+        if S:
+            self._check(self.lib.nb_window_gather_f32(self._p(pos_d), self._p(vel_d), B, rows, N, int(n_states),
+                                                      int(sequence_length), int(stride), self._p(inputs),
+                                                      self._p(targets), self._stream()))
+            self.launches += 1
+        return inputs, targets
 
     def energy_slab(self, pos_d, vel_d, m_d, masses_f32: int, n: int, i0: int, n_i: int, softening: float):
         torch = _torch()

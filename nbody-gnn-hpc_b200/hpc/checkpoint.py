@@ -220,6 +220,16 @@ def sliding_windows(positions: np.ndarray, velocities: np.ndarray, n_steps: int,
     return inputs, targets
 
 
+def sliding_windows_device(positions, velocities, n_steps: int, sequence_length: int, stride: int = 1, device=None):
+    """The sample loop of the reference (checkpoint.py:362-384) for B trajectories whose float64 stacks
+    (B, rows, N, 3) are torch CUDA tensors -- e.g. ``simulate_ensemble(..., outputs="device")``: returns
+    (inputs (B*S, L, N, 6), targets (B*S, N, 6)) float32 CUDA tensors, trajectory-major, i.e. the 'inputs' and
+    'targets' datasets of the reference's dataset file.  One launch of the window kernel (K5, csrc/nb_windows.cu)."""
+    from . import _cuda
+    eng = _cuda.get_engine(device if device is not None else positions.device.index)
+    return eng.window_gather(positions, velocities, int(n_steps), int(sequence_length), int(stride))
+
+
 def create_training_dataset(trajectories: List[Dict], output_path: str, sequence_length: int = 10, stride: int = 1,
                             masses: Optional[np.ndarray] = None) -> str:
     """(input sequence, next state) pairs of all trajectories in one HDF5 file (reference :302-398)."""

@@ -18,17 +18,22 @@ __all__ = ["simulate_ensemble", "generate_simulations", "generate_single_simulat
 
 def simulate_ensemble(positions, velocities, masses, dt: float = 1e-3, softening: float = nbody.SOFTENING,
                       n_steps: int = 400, save_interval: int = 1, *, dtype=None, accelerations=None,
-                      snapshots: bool = True, device=None) -> dict:
+                      snapshots: bool = True, device=None, outputs: str = "host") -> dict:
     """Advance B independent systems of N bodies by n_steps kick-drift-kick steps.
 
     positions, velocities: (B,N,3); masses: (N,) shared by all systems or (B,N).
     Returns float64 arrays: 'positions', 'velocities', 'accelerations' of shape
     (B, 1 + n_steps//save_interval, N, 3) -- per system exactly what the reference's
     ``np.stack([s[key] for s in sim.run(...)])`` yields -- plus 'times' and the final state.
+    outputs="device" leaves the stacks in HBM as torch tensors (72*N bytes per system-step never cross PCIe):
+    the input of the window kernel (``hpc.checkpoint.sliding_windows_device``) and of anything else on the GPU.
     """
+    if outputs not in ("host", "device"):
+        raise ValueError("outputs must be 'host' or 'device'")
     eng = nbody._backend_override or nbody._cuda.get_engine(device)
+    kw = {"outputs": outputs} if outputs != "host" else {}
     out = eng.ensemble(positions, velocities, masses, float(dt), float(softening), int(n_steps), int(save_interval),
-                       dtype=nbody._engine_dtype(dtype), a0=accelerations, snapshots=snapshots)
+                       dtype=nbody._engine_dtype(dtype), a0=accelerations, snapshots=snapshots, **kw)
     t, times = 0.0, [0.0]
     for k in range(1, n_steps + 1):
         t += dt                                   # running sum, reference nbody.py:217

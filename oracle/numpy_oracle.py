@@ -43,3 +43,26 @@ def step_numpy(positions, velocities, accelerations, masses, dt: float, softenin
     a = accel_rows_numpy(x, masses, np.arange(x.shape[0]), softening)   # :211
     v += 0.5 * dt * a                                  # :214
     return x, v, a
+
+
+def window_count(n_states: int, sequence_length: int, stride: int = 1) -> int:
+    """Samples one trajectory yields: len(range(0, n_steps - L, stride)), checkpoint.py:365 (the pre-count at :333,
+    (n_steps - L) // stride, is one short when stride does not divide n_steps - L; the loop is what writes)."""
+    return len(range(0, n_states - sequence_length, stride))
+
+
+def sliding_windows(positions, velocities, n_states: int, sequence_length: int, stride: int = 1):
+    """The sample loop of create_training_dataset, /root/reference/src/hpc/checkpoint.py:362-384, for one trajectory:
+    inputs (S, L, N, 6) float32, targets (S, N, 6) float32.  Plain loop, as in the reference."""
+    positions = np.asarray(positions)
+    velocities = np.asarray(velocities)
+    n = positions.shape[1]
+    ins, tgs = [], []
+    for i in range(0, n_states - sequence_length, stride):                                  # :365
+        ins.append(np.concatenate([positions[i:i + sequence_length],
+                                   velocities[i:i + sequence_length]], axis=-1).astype(np.float32))   # :367-370
+        tgs.append(np.concatenate([positions[i + sequence_length],
+                                   velocities[i + sequence_length]], axis=-1).astype(np.float32))     # :373-376
+    if not ins:
+        return np.zeros((0, sequence_length, n, 6), np.float32), np.zeros((0, n, 6), np.float32)
+    return np.stack(ins), np.stack(tgs)

@@ -378,3 +378,26 @@ def test_ensemble_two_lanes_float32_and_n200(engine, oracle_mod):
             small = simulate_ensemble(x0[lo:lo + 30], v0[lo:lo + 30], m32, dtype=dtype, **kw)   # one lane, 30 CTAs
             for key in ("positions", "velocities", "accelerations", "final_positions"):
                 assert np.array_equal(out[key][lo:lo + 30], small[key]), (dtype, lo, key)
+
+
+@pytest.mark.parametrize("save_interval", [1, 4])
+def test_ensemble_chunked_drain_equals_one_launch(engine, oracle_mod, monkeypatch, save_interval):
+    """The bench's end-to-end path: outputs of 32 MB and more are produced by several launches (step chunks whose
+    snapshot rows drain to pinned host memory while the next chunk runs; every launch re-enters the systems from
+    their parked state with its own snap_offset).  Must equal the single-launch result bit for bit, and the oracle."""
+    from hpc import ics
+    from hpc.ensemble import simulate_ensemble
+    B, N, T = 300, 200, 64
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, N, seed=77)
+    kw = dict(dt=1e-3, n_steps=T, save_interval=save_interval)
+    monkeypatch.setenv("NBODY_D2H_CHUNKS", "8")
+    chunked = simulate_ensemble(x0, v0, m32, **kw)
+    monkeypatch.setenv("NBODY_D2H_CHUNKS", "1")
+    single = simulate_ensemble(x0, v0, m32, **kw)
+    assert chunked["positions"].shape == (B, 1 + T // save_interval, N, 3)
+    for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities", "final_accelerations"):
+        assert np.array_equal(chunked[key], single[key]), key
+    for b in (0, 151, B - 1):
+        chk = oracle_mod.run(x0[b], v0[b], oracle_mod.accel_direct(x0[b], m32, 1e-9), m32, 1e-3, 1e-9, T, save_interval)
+        k = min(chunked["positions"].shape[1], 1 + 48 // save_interval)  # the default ICs are chaotic: first 48 steps
+        assert np.abs(chunked["positions"][b, :k] - chk["positions"][:k]).max() < POS_TOL

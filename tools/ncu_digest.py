@@ -65,7 +65,10 @@ def main():
             "source": f"profiles/{tag}_ncu_full_summary.csv (ncu --set full --clock-control none --import-source on, {cmd})",
         }
     (ROOT / "profiles" / f"{tag}_ncu_full_summary.csv").write_text(out.getvalue())
-    (ROOT / "profiles" / "summary.json").write_text(json.dumps(digest, indent=1) + "\n")
+    summary = ROOT / "profiles" / "summary.json"
+    merged = json.loads(summary.read_text()) if summary.exists() else {}
+    merged.update(digest)  # kernels of other captures are kept
+    summary.write_text(json.dumps(merged, indent=1) + "\n")
     print(json.dumps({k: (round(v["duration_ms"], 3), round(v["pipe_fp64_pct"] or v["pipe_fma_pct"], 1)) for k, v in digest.items()}))
 
 

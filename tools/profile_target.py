@@ -36,4 +36,12 @@ if "ens" in which or "ens400" in which:
         eng.ensemble_device(x, v, a, m_d, f32, 0, B, 200, 1e-3, 1e-9, steps, 1, np.float64, True, True, ox, ov, oa,
                             steps + 1, 0)
     torch.cuda.synchronize()
+if "win" in which:
+    B, rows, N = 300, 401, 200
+    g = torch.Generator(device=eng.device).manual_seed(1)
+    pos = torch.randn((B, rows, N, 3), dtype=torch.float64, device=eng.device, generator=g)
+    vel = torch.randn((B, rows, N, 3), dtype=torch.float64, device=eng.device, generator=g)
+    for _ in range(2):
+        eng.window_gather(pos, vel, rows, 10, 1)
+    torch.cuda.synchronize()
 print("ok")
