@@ -47,7 +47,7 @@ def main():
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         w.writerow([d["Kernel Name"], d["Block Size"], d["Grid Size"]] + [d[c] for c in cols])
-        key = d["Kernel Name"].split("<")[0].replace("void ", "").strip()
+        key = d["Kernel Name"].split("<")[0].split("(")[0].replace("void ", "").strip()
 
         def val(name, scale=True):
             x = float(d[name])
