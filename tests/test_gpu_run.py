@@ -401,3 +401,21 @@ def test_ensemble_chunked_drain_equals_one_launch(engine, oracle_mod, monkeypatc
         chk = oracle_mod.run(x0[b], v0[b], oracle_mod.accel_direct(x0[b], m32, 1e-9), m32, 1e-3, 1e-9, T, save_interval)
         k = min(chunked["positions"].shape[1], 1 + 48 // save_interval)  # the default ICs are chaotic: first 48 steps
         assert np.abs(chunked["positions"][b, :k] - chk["positions"][:k]).max() < POS_TOL
+
+
+@pytest.mark.parametrize("n", [33, 600, 1024])
+def test_ensemble_two_lanes_other_body_counts(engine, n):
+    """Two lanes at the runtime-shape build: an odd small N, one j-part (N > 512) and the shared-memory limit, where
+    two lanes only just fit; equal to one-lane batches bit for bit."""
+    from hpc.ensemble import simulate_ensemble
+    rng = np.random.RandomState(n)
+    B = 2 * engine.sm_count + 5
+    x0 = rng.rand(B, n, 3) * 4 - 2
+    v0 = rng.rand(B, n, 3) - 0.5
+    m = rng.uniform(1e9, 1e10, n)
+    kw = dict(dt=1e-3, softening=0.05, n_steps=5, save_interval=2)
+    big = simulate_ensemble(x0, v0, m, **kw)
+    for lo in (0, B - 20):
+        small = simulate_ensemble(x0[lo:lo + 20], v0[lo:lo + 20], m, **kw)
+        for key in ("positions", "velocities", "accelerations", "final_positions", "final_accelerations"):
+            assert np.array_equal(big[key][lo:lo + 20], small[key]), (n, lo, key)
