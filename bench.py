@@ -294,13 +294,20 @@ def bench_ensemble(args, world, rank, local):
     achieved_tf = inter_step * FLOPS_PER_INTERACTION / k_mean / 1e12
     snap_bytes = B * n_snap * N * 72.0
     prof = profile_summary().get("ensemble_kernel", {})
+    probe_tf = eng.fma_peak_tflops("dfma" if dtype == np.float64 else "ffma")
+    ops_per_inter = 16 if dtype == np.float64 else 12
     roofline = {
         "kernel": f"ensemble_kernel<{'double' if dtype == np.float64 else 'float'}>", "bound": pipe,
         "achieved": round(achieved_tf, 3), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 4),
         "peak_source": f"{eng.sm_count} SMs x {lanes} lanes x 2 x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                        f"{FLOPS_PER_INTERACTION:.0f} flop/interaction convention",
-        "peak_probe": round(eng.fma_peak_tflops("dfma" if dtype == np.float64 else "ffma"), 2),
+        "peak_probe": round(probe_tf, 2),
+        # what the pipe actually executes: 16 FP64 (12 FP32) pipe operations per interaction, against the FMA rate a
+        # pure-FMA probe kernel reaches on this GPU (peak_probe counts 2 flop per FMA)
+        "pipe": {"ops_per_interaction": ops_per_inter, "achieved_Tops": round(inter_step * ops_per_inter / k_mean / 1e12, 3),
+                 "probe_Tops": round(probe_tf / 2, 3),
+                 "frac_of_probe": round(inter_step * ops_per_inter / k_mean / 1e12 / (probe_tf / 2), 4)},
         "kernel_ms": round(k_mean * 1e3, 4),
         "traffic": prof.get("dram_bytes_per_launch"),
         "hbm": {"algorithmic_bytes": snap_bytes, "achieved": round(snap_bytes / k_mean / 1e9, 1),
