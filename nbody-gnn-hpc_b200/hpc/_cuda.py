@@ -389,7 +389,12 @@ class Engine:
             mass_stride = N
         else:
             raise ValueError(f"masses must be (N,) or (B,N); got {m.shape}")
+        if outputs not in ("host", "device"):
+            raise ValueError("outputs must be 'host' or 'device'")
         if N > int(self.lib.nb_ensemble_max_bodies()):
+            if outputs == "device":
+                raise NotImplementedError("device-resident outputs need systems that fit one CTA's shared memory "
+                                          f"(N <= {int(self.lib.nb_ensemble_max_bodies())})")
             # systems too large for one CTA's shared memory: each fills the GPU on its own (K1/K2), one after the other
             outs = []
             for b in range(B):

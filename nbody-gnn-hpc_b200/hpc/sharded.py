@@ -132,7 +132,7 @@ class ShardedSystem:
         if n_steps <= 0:
             return
         eng = self.eng
-        if self.world == 1:
+        if self.world == 1 and hasattr(eng, "run_device"):
             # one GPU: the whole loop is enqueued by one C call (no per-step Python between launches)
             in_a = eng.run_device(self.cur, self.nxt, self.vel, self.acc, self.n, self.dt, self.softening, n_steps,
                                   save_interval, snap_pos, snap_vel, snap_acc, self.ws)
