@@ -34,6 +34,14 @@
 // them stalls; and with both lanes integrated by all warps in lock step nothing overlaps either:
 // 5.42 ms against 5.57 ms for 296 systems; profiles/r01_exp_ens_*.log.)
 //
+// Few systems (8 x B <= SMs; a single simulation is the reference's README default): one system per
+// thread-block CLUSTER of 8 CTAs (cluster_ensemble_kernel).  Every CTA keeps ALL positions of its
+// system in its own shared memory (two buffers), owns an eighth of the bodies -- force phase over
+// all j from local shared memory, integrate phase for its own bodies -- and stores the drifted
+// positions of its bodies straight into the next buffer of all 8 CTAs through distributed shared
+// memory; one barrier.cluster per step, nothing but snapshots touches global memory.  Same j-parts,
+// same summation order: bit-identical to the one-CTA kernel, about a fifth of its time per step.
+//
 // Scheduling.  The grid is persistent, one CTA per SM, `lanes` workers per CTA.  The B x n_steps
 // system-steps of the launch are laid on one line, system-major, and cut into equal intervals, one
 // per worker.  A system that straddles a cut is shared by two neighbouring workers: worker w runs
@@ -43,9 +51,14 @@
 // time when the tail is wanted: all workers advance in lock step (same code, one CTA per SM), so
 // nobody waits, every worker gets the same work to within one step, and 300 systems on 296 workers
 // cost 300/296 of 296 systems (measured: 5.72 -> 5.80 ms) instead of a second round.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "nb_common.cuh"
 
 namespace nb {
+
+namespace cg = cooperative_groups;
 
 template <bool kZeroEps>
 __device__ __forceinline__ void pair_any(double xi, double yi, double zi, double xj, double yj, double zj, double gmj,
@@ -446,6 +459,141 @@ ensemble_kernel(const EnsembleArgs g) {
             if (publish_b[L] >= 0) atomicExch(g.progress + publish_b[L], 1);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// One system per cluster of kClusterCtas CTAs (few systems: 8 x B <= SMs).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kClusterCtas = 8;  // the portable maximum
+
+// shared memory of one CTA of a cluster: two full position buffers, partial slabs / vel / acc of its own slab
+template <typename T>
+__host__ __device__ inline size_t cluster_smem_bytes(int N, int parts) {
+    const int S = (N + kClusterCtas - 1) / kClusterCtas;
+    return 2 * (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(parts + 2) * 3 * S * sizeof(T);
+}
+
+template <typename T, bool kZeroEps>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024, 1)
+cluster_ensemble_kernel(const EnsembleArgs g) {
+    using V4 = typename Vec4<T>::type;
+    extern __shared__ __align__(16) char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int n_clusters = gridDim.x / kClusterCtas, cid = blockIdx.x / kClusterCtas;
+    const int N = g.N, n3 = 3 * N, parts = g.parts;
+    const int S = (N + kClusterCtas - 1) / kClusterCtas;      // bodies per CTA
+    const int i_lo = min(N, rank * S), ns = min(N, i_lo + S) - i_lo;
+    const int tid = threadIdx.x;
+    V4* const pos0 = reinterpret_cast<V4*>(smem);              // buffer c is pos0 + c * N
+    T* part = reinterpret_cast<T*>(pos0 + 2 * N);               // parts x 3S
+    T* vel = part + (size_t)parts * 3 * S;                      // 3S, (body, component) order
+    T* acc = vel + 3 * S;
+    // every CTA's copy of the two position buffers, as seen from here (distributed shared memory)
+    T* remote[kClusterCtas];  // buffer 0 of CTA t; buffer 1 follows it at + 4 N
+#pragma unroll
+    for (int t = 0; t < kClusterCtas; ++t) remote[t] = reinterpret_cast<T*>(cluster.map_shared_rank(pos0, t));
+    const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
+    // force phase: one body of the slab and one j-part per thread (the j-parts of the one-CTA kernel: same sums)
+    const int q = tid / S, li_f = tid - q * S;
+    const bool f_active = q < parts && li_f < ns;
+    const int jb = (int)(((long)q * N) / parts), je = (int)(((long)(q + 1) * N) / parts);
+
+    for (int b = cid; b < g.B; b += n_clusters) {
+        const size_t sbase = (size_t)b * n3;
+        // all positions and G*m into both local buffers; velocity and acceleration of the own slab
+        for (int idx = tid; idx < n3; idx += blockDim.x) {
+            const int i = idx / 3, c = idx - 3 * i;
+            const T xv = (T)__ldcg(&g.x[sbase + idx]);
+            reinterpret_cast<T*>(pos0)[4 * i + c] = xv;
+            reinterpret_cast<T*>(pos0 + N)[4 * i + c] = xv;
+        }
+        for (int i = tid; i < N; i += blockDim.x) {
+            const size_t mi = (size_t)b * g.mass_stride + i;
+            const double m = g.masses_are_f32 ? (double)static_cast<const float*>(g.masses)[mi]
+                                              : static_cast<const double*>(g.masses)[mi];
+            const T gm = (T)(kG * m);  // G * masses[j], nbody.py:57
+            reinterpret_cast<T*>(pos0)[4 * i + 3] = gm;
+            reinterpret_cast<T*>(pos0 + N)[4 * i + 3] = gm;
+        }
+        for (int idx = tid; idx < 3 * ns; idx += blockDim.x) {
+            vel[idx] = (T)__ldcg(&g.v[sbase + 3 * i_lo + idx]);
+            acc[idx] = (T)__ldcg(&g.a[sbase + 3 * i_lo + idx]);
+        }
+        // nobody stores into a neighbour's buffer before that neighbour has finished loading (and finished the
+        // previous system)
+        cluster.sync();
+        int cur = 0;
+        for (int k = 0; k <= g.n_steps; ++k) {
+            const bool do_force = (k > 0) || g.compute_a0;
+            const bool do_close = k > 0;
+            const bool do_open = k < g.n_steps;
+            long srow = -1;  // get_state() before the loop and every save_interval steps, nbody.py:235,240-241
+            if (g.out_x) {
+                if (k == 0) {
+                    if (g.write_initial) srow = g.snap_offset;
+                } else if ((k % g.save_interval) == 0) {
+                    srow = g.snap_offset + (g.write_initial ? 1 : 0) + (k / g.save_interval - 1);
+                }
+            }
+            if (do_force) {
+                if (f_active) {
+                    const V4* pos = pos0 + (size_t)cur * N;
+                    const V4 me = pos[i_lo + li_f];
+                    T ax = 0, ay = 0, az = 0;
+#pragma unroll 4
+                    for (int j = jb; j < je; ++j) {
+                        const V4 pj = pos[j];
+                        pair_any<kZeroEps>(me.x, me.y, me.z, pj.x, pj.y, pj.z, pj.w, eps2, ax, ay, az);
+                    }
+                    T* pa = part + (size_t)q * 3 * S + 3 * li_f;
+                    pa[0] = ax; pa[1] = ay; pa[2] = az;
+                }
+                __syncthreads();
+            }
+            const size_t orow = srow >= 0 ? ((size_t)b * g.n_snap_total + (size_t)srow) * n3 + 3 * i_lo : 0;
+            const T* pos_cur = reinterpret_cast<const T*>(pos0 + (size_t)cur * N);
+            for (int idx = tid; idx < 3 * ns; idx += blockDim.x) {
+                const int li = idx / 3, c = idx - 3 * li;
+                T a = acc[idx];
+                if (do_force) {
+                    a = part[idx];
+                    for (int p = 1; p < parts; ++p) a += part[(size_t)p * 3 * S + idx];
+                    acc[idx] = a;
+                }
+                T v = vel[idx];
+                T x = pos_cur[4 * (i_lo + li) + c];
+                if (do_close) v = mul_add_unfused(half_dt, a, v);  // closing kick, nbody.py:214
+                if (srow >= 0) {
+                    g.out_x[orow + idx] = (double)x;
+                    g.out_v[orow + idx] = (double)v;
+                    g.out_a[orow + idx] = (double)a;
+                }
+                if (do_open) {
+                    v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
+                    x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
+                    const size_t slot = (size_t)(cur ^ 1) * 4 * N + 4 * (i_lo + li) + c;
+#pragma unroll
+                    for (int t = 0; t < kClusterCtas; ++t) remote[t][slot] = x;
+                }
+                vel[idx] = v;
+            }
+            if (do_open) {
+                cluster.sync();  // the next buffer is complete in every CTA; everybody is done reading this one
+                cur ^= 1;
+            }
+        }
+        // final state of the own slab
+        const T* pos_fin = reinterpret_cast<const T*>(pos0 + (size_t)cur * N);
+        for (int idx = tid; idx < 3 * ns; idx += blockDim.x) {
+            const int li = idx / 3, c = idx - 3 * li;
+            g.x[sbase + 3 * i_lo + idx] = (double)pos_fin[4 * (i_lo + li) + c];
+            g.v[sbase + 3 * i_lo + idx] = (double)vel[idx];
+            g.a[sbase + 3 * i_lo + idx] = (double)acc[idx];
+        }
+        __syncthreads();  // the local buffers are reloaded for the next system
+    }
+    cluster.sync();  // no CTA exits while a neighbour may still store into its shared memory
+}
+
 constexpr int kEnsembleMaxBodies = 1024;
 
 template <typename T>
@@ -483,6 +631,29 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     NB_CUDA_OK(cudaGetDevice(&dev));
     NB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     NB_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // Few systems: one system per cluster of 8 CTAs (distributed shared memory), if the slab shape fits a CTA.
+    {
+        const int S = ceil_div(N, kClusterCtas);
+        const int c_threads = round_up(S * parts > 3 * S ? S * parts : 3 * S, 32);
+        const size_t c_smem = cluster_smem_bytes<T>(N, parts);
+        if (B * kClusterCtas <= sms && N >= 2 * kClusterCtas && c_threads <= 1024 && c_smem + 1024 <= (size_t)smem_max &&
+            getenv("NB_ENSEMBLE_NO_CLUSTER") == nullptr) {
+            void (*ck)(const EnsembleArgs) = zero ? cluster_ensemble_kernel<T, true> : cluster_ensemble_kernel<T, false>;
+            NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(B * kClusterCtas);
+            cfg.blockDim = dim3(c_threads);
+            cfg.dynamicSmemBytes = c_smem;
+            cfg.stream = st;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= 1) {
+                g.lanes = 1; g.progress = nullptr;
+                ck<<<B * kClusterCtas, c_threads, c_smem, st>>>(g);
+                return check_launch("cluster ensemble kernel");
+            }
+            (void)cudaGetLastError();  // clusters of 8 cannot be placed (MIG slice, ...): the one-CTA kernel below
+        }
+    }
     // Two lanes + the integrator warp when there are systems for 2 x SMs workers and both lanes fit in shared
     // memory; else one lane, every thread in both phases.
     const size_t lane_bytes = lane_smem_bytes<T>(N, parts);

@@ -25,7 +25,9 @@ NB_STEP_PEER_SYNC = 4
 
 # N at or below which a single system runs through the one-launch ensemble kernel (K3, B = 1)
 # instead of one force launch per step (K1/K2).
-SMALL_SYSTEM_MAX_BODIES = 320    # measured crossover on B200: K3 (B=1) 12-26 us/step at N=256-384, K2 floor 13-21 us
+# Measured on B200 (tools/probe_small.py, fp64 / fp32 us per step): K3 on a cluster of 8 CTAs 3.0 / 2.1 at N = 200,
+# 11.0 / 5.6 at N = 512, 29.5 / 13.9 at N = 768; K2 18.6 / 10.8 at N = 512, 18.9 / 11.1 at N = 768.
+SMALL_SYSTEM_MAX_BODIES = 640
 
 
 class EngineUnavailable(RuntimeError):

@@ -419,3 +419,25 @@ def test_ensemble_two_lanes_other_body_counts(engine, n):
         small = simulate_ensemble(x0[lo:lo + 20], v0[lo:lo + 20], m, **kw)
         for key in ("positions", "velocities", "accelerations", "final_positions", "final_accelerations"):
             assert np.array_equal(big[key][lo:lo + 20], small[key]), (n, lo, key)
+
+
+@pytest.mark.parametrize("n,dtype", [(16, "float64"), (17, "float64"), (200, "float64"), (200, "float32"),
+                                     (257, "float64"), (600, "float32"), (1024, "float64")])
+def test_cluster_kernel_bitwise_equals_one_cta_kernel(engine, monkeypatch, n, dtype):
+    """Few systems run one per cluster of 8 CTAs (distributed shared memory, one barrier.cluster per step); the
+    j-parts and every sum are those of the one-CTA kernel, so the results are the same bits -- also with slabs that
+    do not divide (N = 17: two CTAs of the cluster own nothing), per-system masses, n_steps = 0 and given a_0."""
+    from hpc.ensemble import simulate_ensemble
+    rng = np.random.RandomState(n)
+    B = 3
+    x0 = rng.rand(B, n, 3) * 4 - 2
+    v0 = rng.rand(B, n, 3) - 0.5
+    m = rng.uniform(1e9, 1e10, (B, n))
+    a0 = rng.rand(B, n, 3)
+    for kw in (dict(n_steps=7, save_interval=2), dict(n_steps=0, save_interval=1), dict(n_steps=5, save_interval=1, accelerations=a0)):
+        monkeypatch.delenv("NB_ENSEMBLE_NO_CLUSTER", raising=False)
+        clu = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, dtype=dtype, **kw)
+        monkeypatch.setenv("NB_ENSEMBLE_NO_CLUSTER", "1")
+        one = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, dtype=dtype, **kw)
+        for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities", "final_accelerations"):
+            assert np.array_equal(clu[key], one[key]), (n, dtype, kw.get("n_steps"), key)
