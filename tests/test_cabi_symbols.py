@@ -21,7 +21,8 @@ def test_header_declares_the_expected_surface():
     names = declared_functions()
     for required in ("nb_accel_f32", "nb_accel_f64", "nb_step_f32", "nb_step_f64", "nb_run_f64", "nb_ensemble_f64",
                      "nb_ensemble_f32", "nb_energy_f64", "nb_pack_f32", "nbh_accel_direct", "nbh_run",
-                     "nbh_ensemble_run", "nbh_total_energy", "nb_last_error"):
+                     "nbh_ensemble_run", "nbh_total_energy", "nb_last_error", "nb_window_gather_f32", "nb_window_count",
+                     "nb_step_peer_f32", "nb_step_peer_f64"):
         assert required in names
     text = HEADER.read_text()
     assert "torch" not in text.lower().replace("pytorch", "")     # plain pointers and sizes only
