@@ -115,7 +115,7 @@ def cpu_ensemble_sample(n_sims: int, seed0: int = 42):
     import oracle
     from hpc import ics
     oracle.build()
-    cores = oracle.num_threads()
+    cores = oracle.use_all_cores()
     x0, v0, m32 = ics.datagen_ensemble_ic(n_sims, ENS_N, seed=seed0)
     oracle.ensemble_run(x0[:cores], v0[:cores], m32, 1e-3, 1e-9, 20, 1, outputs=True)   # warm the threads and pages
     t0 = time.perf_counter()
@@ -130,6 +130,7 @@ def cpu_single_sample(n: int, seed: int = 7):
     import oracle
     from hpc import ics
     oracle.build()
+    oracle.use_all_cores()
     x, _, m = ics.plummer_ic(n, seed=seed)
     oracle.accel_direct(x[:256], m[:256], 0.01)
     t0 = time.perf_counter()
@@ -146,7 +147,7 @@ def run_reference_arm(args) -> None:
         return
     import oracle
     oracle.build()
-    cores = oracle.num_threads()
+    cores = oracle.use_all_cores()
     if args.workload == "ensemble":
         n_sims = max(16 * cores, 32)          # ~1 s of wall time, ~16 core-seconds per step
         sample = f"{n_sims} of {ENS_B} simulations x {ENS_N} bodies x {ENS_STEPS} steps per step, {cores} threads"
@@ -191,8 +192,6 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its banner / NCCL_DEBUG output to stdout by default; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
 
@@ -530,16 +529,24 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    # stdout carries exactly one line, the JSON: whatever libraries print while the bench runs (NCCL's version
+    # banner goes to stdout) is sent to stderr, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     world, rank, local = dist_setup(args.gpus)
     if args.workload == "ensemble":
         line = bench_ensemble(args, world, rank, local)
     else:
         line = bench_single(args, world, rank, local, sharded=(args.workload == "sharded"))
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -94,6 +94,8 @@ def lib() -> ctypes.CDLL:
                              vp, vp, vp, vp, vp, vp, vp]
     L.oracle_ensemble_run.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, ci, ci, vp, vp, vp, vp]
     L.oracle_num_threads.restype = ci
+    L.oracle_set_num_threads.argtypes = [ci]
+    L.oracle_set_num_threads.restype = None
     for name in ("oracle_accel_direct", "oracle_accel_direct_rows", "oracle_accel_direct_serial",
                  "oracle_accel_direct_strict", "oracle_total_energy", "oracle_total_energy_parallel",
                  "oracle_step", "oracle_run", "oracle_ensemble_run"):
@@ -109,6 +111,16 @@ def isa_level() -> str:
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(n)
+    return num_threads()
 
 
 def _f64(a) -> np.ndarray:

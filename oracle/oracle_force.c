@@ -168,6 +168,16 @@ void oracle_total_energy_parallel(const double *pos, const double *vel,
     out[2] = kinetic + potential;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for the cores it really has. */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP
