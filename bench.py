@@ -150,7 +150,8 @@ def run_reference_arm(args) -> None:
     cores = oracle.use_all_cores()
     if args.workload == "ensemble":
         n_sims = max(16 * cores, 32)          # ~1 s of wall time, ~16 core-seconds per step
-        sample = f"{n_sims} of {ENS_B} simulations x {ENS_N} bodies x {ENS_STEPS} steps per step, {cores} threads"
+        sample = (f"{n_sims} simulations of the workload's kind ({ENS_N} bodies x {ENS_STEPS} steps; an ensemble is "
+                  f"{ENS_B} of them) per step, {cores} threads")
         fn = lambda: cpu_ensemble_sample(n_sims)      # noqa: E731
         cfg = {"workload": f"datagen ensemble {ENS_B}x{ENS_N}x{ENS_STEPS} per GPU, fp64 snapshots every step (configs[1])",
                "simulations_per_gpu": ENS_B, "bodies": ENS_N, "sim_steps": ENS_STEPS, "save_interval": 1,
@@ -321,7 +322,8 @@ def bench_ensemble(args, world, rank, local):
         n_sims = 32 * (os.cpu_count() or 8)
         v_cpu, s_cpu, cores = cpu_ensemble_sample(n_sims)
         cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sims} of {B} simulations x {N} bodies x {T} steps, one thread per simulation, {s_cpu:.1f} s"}
+               "sample": f"{n_sims} simulations of the workload's kind ({N} bodies x {T} steps; an ensemble is {B} of them), "
+                         f"one thread per simulation, {s_cpu:.1f} s on {cores} cores"}
     extra = single_system_extras(eng) if (rank == 0 and not args.no_extras) else None
     if extra is not None:
         extra["window_gather_300x401x200_L10"] = window_extras(eng, outs[0][0], outs[0][1])
