@@ -63,6 +63,14 @@ def test_bad_arguments_return_codes_not_crashes():
     rc = lib.nb_ensemble_f64(None, None, None, None, 0, 0, 1, 1, 1e-3, 1e-9, 1, 1, 1, 1, None, None, None, 1, 0,
                              None, 0, None)
     assert rc == 1 and b"null" in lib.nb_last_error()
+    rc = lib.nb_window_gather_f32(None, None, 1, 1, 1, 1, 1, 1, None, None, None)
+    assert rc == 1 and b"null" in lib.nb_last_error()
+    import ctypes
+    buf = ctypes.create_string_buffer(64)
+    rc = lib.nb_window_gather_f32(buf, buf, 1, 4, 2, 9, 2, 1, buf, buf, None)      # n_states > rows
+    assert rc == 1 and b"n_states" in lib.nb_last_error()
+    rc = lib.nb_window_gather_f32(buf, buf, 1, 4, 2, 4, 0, 1, buf, buf, None)      # sequence_length < 1
+    assert rc == 1 and b"sequence_length" in lib.nb_last_error()
 
 
 def test_no_cpu_fallback_and_no_oracle_in_product():
