@@ -34,11 +34,11 @@
 // them stalls; and with both lanes integrated by all warps in lock step nothing overlaps either:
 // 5.42 ms against 5.57 ms for 296 systems; profiles/r01_exp_ens_*.log.)
 //
-// Few systems (8 x B <= SMs; a single simulation is the reference's README default): one system per
-// thread-block CLUSTER of 8 CTAs (cluster_ensemble_kernel).  Every CTA keeps ALL positions of its
-// system in its own shared memory (two buffers), owns an eighth of the bodies -- force phase over
+// Few systems (C x B <= SMs for C = 8, 4 or 2; a single simulation is the reference's README
+// default): one system per thread-block CLUSTER of C CTAs (cluster_ensemble_kernel).  Every CTA keeps
+// ALL positions of its system in its own shared memory (two buffers), owns 1/C of the bodies -- force phase over
 // all j from local shared memory, integrate phase for its own bodies -- and stores the drifted
-// positions of its bodies straight into the next buffer of all 8 CTAs through distributed shared
+// positions of its bodies straight into the next buffer of all C CTAs through distributed shared
 // memory; one barrier.cluster per step, nothing but snapshots touches global memory.  Same j-parts,
 // same summation order: bit-identical to the one-CTA kernel, about a fifth of its time per step.
 //
@@ -460,27 +460,27 @@ ensemble_kernel(const EnsembleArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// One system per cluster of kClusterCtas CTAs (few systems: 8 x B <= SMs).
+// One system per cluster of C = 8, 4 or 2 CTAs (few systems: the largest C with C x B <= SMs).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kClusterCtas = 8;  // the portable maximum
+constexpr int kClusterCtas = 8;  // the portable maximum; the launch may use 4 or 2
 
 // shared memory of one CTA of a cluster: two full position buffers, partial slabs / vel / acc of its own slab
 template <typename T>
-__host__ __device__ inline size_t cluster_smem_bytes(int N, int parts) {
-    const int S = (N + kClusterCtas - 1) / kClusterCtas;
+__host__ __device__ inline size_t cluster_smem_bytes(int N, int parts, int C) {
+    const int S = (N + C - 1) / C;
     return 2 * (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(parts + 2) * 3 * S * sizeof(T);
 }
 
 template <typename T, bool kZeroEps>
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024, 1)
-cluster_ensemble_kernel(const EnsembleArgs g) {
+__global__ void __launch_bounds__(1024, 1) cluster_ensemble_kernel(const EnsembleArgs g) {
     using V4 = typename Vec4<T>::type;
     extern __shared__ __align__(16) char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int n_clusters = gridDim.x / kClusterCtas, cid = blockIdx.x / kClusterCtas;
+    const int C = (int)cluster.num_blocks();                    // cudaLaunchAttributeClusterDimension of the launch
+    const int n_clusters = gridDim.x / C, cid = blockIdx.x / C;
     const int N = g.N, n3 = 3 * N, parts = g.parts;
-    const int S = (N + kClusterCtas - 1) / kClusterCtas;      // bodies per CTA
+    const int S = (N + C - 1) / C;                              // bodies per CTA
     const int i_lo = min(N, rank * S), ns = min(N, i_lo + S) - i_lo;
     const int tid = threadIdx.x;
     V4* const pos0 = reinterpret_cast<V4*>(smem);              // buffer c is pos0 + c * N
@@ -490,7 +490,7 @@ cluster_ensemble_kernel(const EnsembleArgs g) {
     // every CTA's copy of the two position buffers, as seen from here (distributed shared memory)
     T* remote[kClusterCtas];  // buffer 0 of CTA t; buffer 1 follows it at + 4 N
 #pragma unroll
-    for (int t = 0; t < kClusterCtas; ++t) remote[t] = reinterpret_cast<T*>(cluster.map_shared_rank(pos0, t));
+    for (int t = 0; t < kClusterCtas; ++t) remote[t] = reinterpret_cast<T*>(cluster.map_shared_rank(pos0, t < C ? t : 0));
     const T dt = (T)g.dt, half_dt = (T)g.half_dt, eps2 = (T)g.eps2;
     // force phase: one body of the slab and one j-part per thread (the j-parts of the one-CTA kernel: same sums)
     const int q = tid / S, li_f = tid - q * S;
@@ -572,7 +572,8 @@ cluster_ensemble_kernel(const EnsembleArgs g) {
                     x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
                     const size_t slot = (size_t)(cur ^ 1) * 4 * N + 4 * (i_lo + li) + c;
 #pragma unroll
-                    for (int t = 0; t < kClusterCtas; ++t) remote[t][slot] = x;
+                    for (int t = 0; t < kClusterCtas; ++t)
+                        if (t < C) remote[t][slot] = x;
                 }
                 vel[idx] = v;
             }
@@ -631,28 +632,35 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     NB_CUDA_OK(cudaGetDevice(&dev));
     NB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     NB_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // Few systems: one system per cluster of 8 CTAs (distributed shared memory), if the slab shape fits a CTA.
-    {
-        const int S = ceil_div(N, kClusterCtas);
+    // Few systems: one system per cluster of 8, 4 or 2 CTAs (distributed shared memory) -- the largest cluster that
+    // still gives every system its own -- if the slab shape fits a CTA.
+    for (int C = kClusterCtas; C >= 2 && getenv("NB_ENSEMBLE_NO_CLUSTER") == nullptr; C /= 2) {
+        if ((long)B * C > sms) continue;
+        const int S = ceil_div(N, C);
         const int c_threads = round_up(S * parts > 3 * S ? S * parts : 3 * S, 32);
-        const size_t c_smem = cluster_smem_bytes<T>(N, parts);
-        if (B * kClusterCtas <= sms && N >= 2 * kClusterCtas && c_threads <= 1024 && c_smem + 1024 <= (size_t)smem_max &&
-            getenv("NB_ENSEMBLE_NO_CLUSTER") == nullptr) {
-            void (*ck)(const EnsembleArgs) = zero ? cluster_ensemble_kernel<T, true> : cluster_ensemble_kernel<T, false>;
-            NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(B * kClusterCtas);
-            cfg.blockDim = dim3(c_threads);
-            cfg.dynamicSmemBytes = c_smem;
-            cfg.stream = st;
-            int n_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= 1) {
-                g.lanes = 1; g.progress = nullptr;
-                ck<<<B * kClusterCtas, c_threads, c_smem, st>>>(g);
-                return check_launch("cluster ensemble kernel");
-            }
-            (void)cudaGetLastError();  // clusters of 8 cannot be placed (MIG slice, ...): the one-CTA kernel below
+        const size_t c_smem = cluster_smem_bytes<T>(N, parts, C);
+        if (N < 2 * C || c_threads > 1024 || c_smem + 1024 > (size_t)smem_max) continue;
+        void (*ck)(const EnsembleArgs) = zero ? cluster_ensemble_kernel<T, true> : cluster_ensemble_kernel<T, false>;
+        NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B * C);
+        cfg.blockDim = dim3(c_threads);
+        cfg.dynamicSmemBytes = c_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= 1) {
+            g.lanes = 1; g.progress = nullptr;
+            NB_CUDA_OK(cudaLaunchKernelEx(&cfg, ck, g));
+            return check_launch("cluster ensemble kernel");
         }
+        (void)cudaGetLastError();  // clusters of this size cannot be placed (MIG slice, ...): try smaller, then one CTA
     }
     // Two lanes + the integrator warp when there are systems for 2 x SMs workers and both lanes fit in shared
     // memory; else one lane, every thread in both phases.

@@ -441,3 +441,19 @@ def test_cluster_kernel_bitwise_equals_one_cta_kernel(engine, monkeypatch, n, dt
         one = simulate_ensemble(x0, v0, m, dt=1e-3, softening=0.05, dtype=dtype, **kw)
         for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities", "final_accelerations"):
             assert np.array_equal(clu[key], one[key]), (n, dtype, kw.get("n_steps"), key)
+
+
+@pytest.mark.parametrize("B", [10, 18, 19, 37, 38, 74, 75])
+def test_cluster_sizes_bitwise_equal_one_cta_kernel(engine, monkeypatch, B):
+    """The launch gives every system the largest cluster (8, 4 or 2 CTAs) that C x B <= SMs allows -- 10 systems
+    (evaluate.py's ground truth) run on clusters of 8, 19..37 on 4, 38..74 on 2, 75 on single CTAs: same bits."""
+    from hpc import ics
+    from hpc.ensemble import simulate_ensemble
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=B)
+    kw = dict(dt=1e-3, n_steps=9, save_interval=3)
+    monkeypatch.delenv("NB_ENSEMBLE_NO_CLUSTER", raising=False)
+    clu = simulate_ensemble(x0, v0, m32, **kw)
+    monkeypatch.setenv("NB_ENSEMBLE_NO_CLUSTER", "1")
+    one = simulate_ensemble(x0, v0, m32, **kw)
+    for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities", "final_accelerations"):
+        assert np.array_equal(clu[key], one[key]), (B, key)
