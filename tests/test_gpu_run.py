@@ -424,7 +424,7 @@ def test_ensemble_two_lanes_other_body_counts(engine, n):
 @pytest.mark.parametrize("n,dtype", [(16, "float64"), (17, "float64"), (200, "float64"), (200, "float32"),
                                      (257, "float64"), (600, "float32"), (1024, "float64")])
 def test_cluster_kernel_bitwise_equals_one_cta_kernel(engine, monkeypatch, n, dtype):
-    """Few systems run one per cluster of 8 CTAs (distributed shared memory, one barrier.cluster per step); the
+    """Few systems run one per cluster of 8 CTAs (positions exchanged by st.async through distributed shared memory); the
     j-parts and every sum are those of the one-CTA kernel, so the results are the same bits -- also with slabs that
     do not divide (N = 17: two CTAs of the cluster own nothing), per-system masses, n_steps = 0 and given a_0."""
     from hpc.ensemble import simulate_ensemble
