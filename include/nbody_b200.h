@@ -168,6 +168,10 @@ int nb_ensemble_max_bodies(void);
 /* Device scratch: one hand-over flag per system, for systems whose steps are shared by two neighbouring workers
  * of the interval schedule (zeroed by the call itself). */
 size_t nb_ensemble_workspace_bytes(int B);
+/* The interval schedule of the ensemble kernel, as host arithmetic (for tests and tooling): the pieces worker w of
+ * n_workers (<= B) runs, in order; out[5*i..5*i+4] = {system, first step, last step, waits for the previous worker's
+ * flag, parks its state for the next worker}; *n_pieces = their number (only the first max_pieces are written). */
+int nb_ensemble_worker_plan(int B, int n_steps, int n_workers, int w, int* out, int max_pieces, int* n_pieces);
 int nb_ensemble_f64(double* x, double* v, double* a, const void* masses, int masses_are_f32, int mass_stride,
                     int B, int N, double dt, double softening, int n_steps, int save_interval,
                     int compute_a0, int write_initial,

@@ -179,7 +179,7 @@ struct Piece {
 // the next worker, whole systems, tail of the system shared with the previous worker (see the header).
 struct Worker {
     int b_first, s_first, b_last, s_last, b_whole, n_steps, stage;
-    __device__ void init(long w, long n_workers, int B, int n_steps_) {
+    __host__ __device__ void init(long w, long n_workers, int B, int n_steps_) {
         n_steps = n_steps_;
         const long n = n_steps_ > 0 ? n_steps_ : 1;  // n_steps == 0 (a_0 / first snapshot only): one unit per system
         const long W = (long)B * n;
@@ -189,7 +189,7 @@ struct Worker {
         b_whole = b_first + (s_first > 0 ? 1 : 0);
         stage = 0;
     }
-    __device__ bool next(Piece& p) {
+    __host__ __device__ bool next(Piece& p) {
         if (stage == 0) {
             stage = 1;
             if (s_last > 0) { p = Piece{b_last, 0, s_last, false, true}; return true; }
@@ -740,6 +740,26 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
 extern "C" {
 
 int nb_ensemble_max_bodies(void) { return nb::kEnsembleMaxBodies; }
+
+// The pieces worker w of n_workers would run, in order (host arithmetic; what the kernel's workers compute for
+// themselves): out[5*i .. 5*i+4] = {system, first step, last step, waits for the previous worker, parks for the next}.
+int nb_ensemble_worker_plan(int B, int n_steps, int n_workers, int w, int* out, int max_pieces, int* n_pieces) {
+    NB_REQUIRE(B > 0 && n_steps >= 0 && n_workers > 0 && n_workers <= B && w >= 0 && w < n_workers && out && n_pieces,
+               "need 0 < n_workers <= B, 0 <= w < n_workers, n_steps >= 0 and output pointers");
+    nb::Worker wk;
+    wk.init(w, n_workers, B, n_steps);
+    nb::Piece p;
+    int n = 0;
+    while (wk.next(p)) {
+        if (n < max_pieces) {
+            out[5 * n + 0] = p.b; out[5 * n + 1] = p.k0; out[5 * n + 2] = p.k1;
+            out[5 * n + 3] = p.wait ? 1 : 0; out[5 * n + 4] = p.publish ? 1 : 0;
+        }
+        ++n;
+    }
+    *n_pieces = n;  // may exceed max_pieces: only the first max_pieces were written
+    return NB_OK;
+}
 
 // per-system hand-over flags
 size_t nb_ensemble_workspace_bytes(int B) { return (sizeof(int) * ((size_t)(B > 0 ? B : 0) + 1) + 255) / 256 * 256; }

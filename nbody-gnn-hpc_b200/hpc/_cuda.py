@@ -63,6 +63,7 @@ _SIGNATURES = {
     "nb_run_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_ensemble_max_bodies": (_ci, []),
     "nb_ensemble_workspace_bytes": (_sz, [_ci]),
+    "nb_ensemble_worker_plan": (_ci, [_ci, _ci, _ci, _ci, _ip, _ci, _ip]),
     "nb_ensemble_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
                               _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
     "nb_ensemble_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
