@@ -493,8 +493,10 @@ __device__ __forceinline__ void st_async(uint32_t remote_addr, float v, uint32_t
                  : "memory");
 }
 
-template <typename T, bool kZeroEps>
-__global__ void __launch_bounds__(1024, 1) cluster_ensemble_kernel(const EnsembleArgs g) {
+// kMaxThreads bounds the launch so that small slabs (N = 200: 128 threads) get the registers to keep many
+// interactions in flight: with one warp per scheduler the force loop is a latency chain, not a throughput problem.
+template <typename T, bool kZeroEps, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const EnsembleArgs g) {
     using V4 = typename Vec4<T>::type;
     extern __shared__ __align__(16) char smem[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(1024, 1) cluster_ensemble_kernel(const Ensembl
                     T ax = 0, ay = 0, az = 0;
                     // one warp per scheduler and one body per thread: the only parallelism is across j, so eight
                     // interactions are kept in flight (the sums still run in ascending j)
-#pragma unroll 8
+#pragma unroll 20
                     for (int j = jb; j < je; ++j) {
                         const V4 pj = pos[j];
                         pair_any<kZeroEps>(me.x, me.y, me.z, pj.x, pj.y, pj.z, pj.w, eps2, ax, ay, az);
@@ -681,7 +683,11 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
         const int c_threads = round_up(S * parts > 3 * S ? S * parts : 3 * S, 32);
         const size_t c_smem = cluster_smem_bytes<T>(N, parts, C);
         if (N < 2 * C || c_threads > 1024 || c_smem + 1024 > (size_t)smem_max) continue;
-        void (*ck)(const EnsembleArgs) = zero ? cluster_ensemble_kernel<T, true> : cluster_ensemble_kernel<T, false>;
+        void (*ck)(const EnsembleArgs);
+        if (c_threads <= 256)
+            ck = zero ? cluster_ensemble_kernel<T, true, 256> : cluster_ensemble_kernel<T, false, 256>;
+        else
+            ck = zero ? cluster_ensemble_kernel<T, true, 1024> : cluster_ensemble_kernel<T, false, 1024>;
         NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(B * C);

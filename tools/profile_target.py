@@ -44,4 +44,24 @@ if "win" in which:
     for _ in range(2):
         eng.window_gather(pos, vel, rows, 10, 1)
     torch.cuda.synchronize()
+if "clu" in which:
+    # one system on a cluster of 8 CTAs (configs[0]) and ten (evaluate.py), 400 steps, snapshots every step
+    for B in (1, 10):
+        x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=42)
+        x, v = eng.to_device(x0), eng.to_device(v0)
+        a = torch.zeros_like(x)
+        m_d, f32 = eng._masses_dev(m32)
+        ox = torch.empty((B, 401, 200, 3), dtype=torch.float64, device=eng.device)
+        ov, oa = torch.empty_like(ox), torch.empty_like(ox)
+        for _ in range(2):
+            eng.ensemble_device(x, v, a, m_d, f32, 0, B, 200, 1e-3, 1e-9, 400, 1, np.float64, True, True, ox, ov, oa, 401, 0)
+        torch.cuda.synchronize()
+if "energy" in which:
+    n = 65536
+    x, v, m = ics.plummer_ic(n, seed=7)
+    pos_d, vel_d = eng.to_device(x), eng.to_device(v)
+    m_d, f32 = eng._masses_dev(m)
+    for _ in range(2):
+        eng.energy_slab(pos_d, vel_d, m_d, f32, n, 0, n, 0.01)
+    torch.cuda.synchronize()
 print("ok")
