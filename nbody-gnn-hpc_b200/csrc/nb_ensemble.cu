@@ -702,12 +702,14 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int n_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= 1) {
+        // every system's cluster must be resident at once (clusters are placed inside a GPC, so fewer fit than
+        // SMs / C: 37 clusters of 4 ran in two waves, 2.1 ms against 1.8 ms on clusters of 2)
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= B) {
             g.lanes = 1; g.progress = nullptr;
             NB_CUDA_OK(cudaLaunchKernelEx(&cfg, ck, g));
             return check_launch("cluster ensemble kernel");
         }
-        (void)cudaGetLastError();  // clusters of this size cannot be placed (MIG slice, ...): try smaller, then one CTA
+        (void)cudaGetLastError();  // not all clusters of this size can be placed at once: try smaller, then one CTA
     }
     // Two lanes + the integrator warp when there are systems for 2 x SMs workers and both lanes fit in shared
     // memory; else one lane, every thread in both phases.
