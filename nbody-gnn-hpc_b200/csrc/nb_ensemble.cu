@@ -293,7 +293,7 @@ __device__ __forceinline__ void force_phase(const EnsembleArgs& g, const SystemS
     const V4 me0 = s.pos[i0];
     const V4 me1 = s.pos[has1 ? i1 : i0];
     T ax0 = 0, ay0 = 0, az0 = 0, ax1 = 0, ay1 = 0, az1 = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = jb; j < je; ++j) {
         const V4 pj = s.pos[j];
         pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
