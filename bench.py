@@ -38,6 +38,27 @@ METRIC = "pairwise interactions/s (1e9)"
 UNIT = "Ginteractions/s"
 FLOPS_PER_INTERACTION = 20.0      # BASELINE.json north_star convention
 ENS_B, ENS_N, ENS_STEPS = 300, 200, 400
+REF_FILE = ROOT / "baseline" / "_ref" / "nbody.py"   # unmodified copy of the reference's src/hpc/nbody.py (git-ignored)
+
+
+def ensemble_config() -> dict:
+    """`config` of the default workload -- the same dict, key for key, in both arms."""
+    return {"workload": f"datagen ensemble {ENS_B}x{ENS_N}x{ENS_STEPS} per GPU, fp64 snapshots every step (configs[1])",
+            "simulations_per_gpu": ENS_B, "bodies": ENS_N, "sim_steps": ENS_STEPS, "save_interval": 1,
+            "ics": "reference-default (seeded uniform box, shared float32 masses)",
+            "l2": "GPU arm: each step writes 1.73 GB of fresh snapshot lines (>> 126 MB L2), two output sets alternate; "
+                  "reference arm: host cores, no GPU cache involved",
+            "parallelism": "simulations split over the ranks, no communication"}
+
+
+def source_hash() -> str:
+    """Hash of the CUDA sources and the C header: profiles/summary.json records the one its captures were taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((PKG / "csrc").glob("*.cu*")) + [ROOT / "include" / "nbody_b200.h"]:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 def measured_peaks() -> dict:
@@ -139,24 +160,138 @@ def cpu_single_sample(n: int, seed: int = 7):
     return n * (n - 1.0) / dt / 1e9, dt, oracle.num_threads()
 
 
+# ---- the reference itself: Numba code of baseline/_ref/nbody.py, one single-threaded process per simulation -----------
+_ref_mod = None
+
+
+def _numba_worker_init(path: str) -> None:
+    """Pool initializer: what scripts/generate_data.py:16-29 does at import time in every worker."""
+    global _ref_mod
+    for k in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_nbody", path)
+    _ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_ref_mod)
+
+
+def _numba_single_simulation(args):
+    """The reference's worker, scripts/generate_data.py:32-58, call for call (that script itself cannot be imported:
+    it pulls in h5py through hpc.checkpoint, which this image lacks).  The result dict goes back through the pool's
+    pipe, as in the reference."""
+    sim_id, n_particles, n_steps, save_interval, box_size, seed, shared_masses = args
+    sim = _ref_mod.NBodySimulator(n_particles=n_particles, box_size=box_size, dt=0.001, seed=seed,
+                                  use_barnes_hut=(n_particles > 500))
+    if shared_masses is not None:
+        sim.masses = shared_masses.copy()
+        sim.accelerations = sim._compute_accelerations()
+    states = sim.run(n_steps, save_interval=save_interval, verbose=False)
+    return {"positions": np.stack([s["positions"] for s in states]),
+            "velocities": np.stack([s["velocities"] for s in states]),
+            "accelerations": np.stack([s["accelerations"] for s in states]),
+            "masses": states[0]["masses"], "times": np.array([s["time"] for s in states]), "n_steps": len(states)}
+
+
+def _numba_api_timings(_=None):
+    """configs[0] through the reference's own simulator in one single-threaded worker: run(400) and the
+    `for ...: sim.step()` loop of scripts/benchmark_bh_temp.py:24,32, N = 200 (JIT already warm)."""
+    masses = np.random.RandomState(42).uniform(1e10, 1e12, ENS_N).astype(np.float32)
+
+    def make():
+        sim = _ref_mod.NBodySimulator(n_particles=ENS_N, box_size=10.0, dt=0.001, seed=42)
+        sim.masses = masses.copy()
+        sim.accelerations = sim._compute_accelerations()
+        return sim
+
+    make().run(20, verbose=False)
+    best_run, best_loop = 1e9, 1e9
+    for _ in range(3):
+        sim = make()
+        t0 = time.perf_counter()
+        sim.run(ENS_STEPS, save_interval=1, verbose=False)
+        best_run = min(best_run, time.perf_counter() - t0)
+        sim = make()
+        t0 = time.perf_counter()
+        for _ in range(ENS_STEPS):
+            sim.step()
+        best_loop = min(best_loop, time.perf_counter() - t0)
+    return best_run * 1e3, best_loop * 1e3
+
+
+class NumbaEnsemble:
+    """The reference's data-generation path on the host cores: mp.Pool(cores) of single-threaded Numba workers
+    (scripts/generate_data.py:16-19,143-147) running the UNMODIFIED src/hpc/nbody.py from baseline/_ref."""
+
+    def __init__(self):
+        import multiprocessing as mp
+        import numba  # noqa: F401  (fail here, not in the workers)
+        if not REF_FILE.exists():
+            raise FileNotFoundError(f"{REF_FILE} (copied from /root/reference by __graft_entry__.build())")
+        self.cores = os.cpu_count() or 1
+        self.version = numba.__version__
+        for k in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[k] = "1"
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_numba_worker_init, initargs=(str(REF_FILE),))
+        self.masses = np.random.RandomState(42).uniform(1e10, 1e12, ENS_N).astype(np.float32)  # generate_data.py:108-109
+        # JIT compilation (about 3 s per worker) happens here, outside every timed region
+        self.run(self.cores, n_steps=2)
+
+    def run(self, n_sims: int, n_steps: int = ENS_STEPS, seed0: int = 42):
+        """n_sims simulations of the datagen kind; returns (Ginteractions/s, seconds)."""
+        args = [(i, ENS_N, n_steps, 1, 10.0, seed0 + i, self.masses) for i in range(n_sims)]
+        t0 = time.perf_counter()
+        trajs = list(self.pool.imap(_numba_single_simulation, args))
+        dt = time.perf_counter() - t0
+        assert len(trajs) == n_sims and trajs[-1]["positions"].shape == (n_steps + 1, ENS_N, 3)
+        return n_sims * n_steps * ENS_N * (ENS_N - 1.0) / dt / 1e9, dt
+
+    def api_timings(self):
+        return self.pool.apply(_numba_api_timings)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_engine():
+    """(kind, runner): the real Numba reference when baseline/_ref/nbody.py and numba are here, else the C port."""
+    try:
+        return "reference", NumbaEnsemble()
+    except Exception as e:                      # noqa: BLE001 -- say why, then fall back to the port
+        sys.stderr.write(f"[bench] Numba reference unavailable ({e!r}); timing the C port of it instead\n")
+        return "port", None
+
+
 def run_reference_arm(args) -> None:
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is Numba-JIT Python
-    and /root/reference does not exist on the GPU box) on the host cores, same metric and config."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same metric and
+    config, one bench step = one whole ensemble of 300 simulations.  The unmodified Numba module from baseline/_ref
+    when it is there (kind "reference"), else the oracle's C port of it (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    oracle.build()
-    cores = oracle.use_all_cores()
+    extra = {}
     if args.workload == "ensemble":
-        n_sims = max(16 * cores, 32)          # ~1 s of wall time, ~16 core-seconds per step
-        sample = (f"{n_sims} simulations of the workload's kind ({ENS_N} bodies x {ENS_STEPS} steps; an ensemble is "
-                  f"{ENS_B} of them) per step, {cores} threads")
-        fn = lambda: cpu_ensemble_sample(n_sims)      # noqa: E731
-        cfg = {"workload": f"datagen ensemble {ENS_B}x{ENS_N}x{ENS_STEPS} per GPU, fp64 snapshots every step (configs[1])",
-               "simulations_per_gpu": ENS_B, "bodies": ENS_N, "sim_steps": ENS_STEPS, "save_interval": 1,
-               "ics": "reference-default (seeded uniform box, shared float32 masses)"}
+        kind, ref = reference_engine()
+        cfg = ensemble_config()
+        if kind == "reference":
+            cores = ref.cores
+            sample = (f"{ENS_B} simulations ({ENS_N} bodies x {ENS_STEPS} steps) per step = one ensemble, mp.Pool({cores}) of "
+                      f"single-threaded Numba workers (generate_data.py:16-19,143-147), numba {ref.version}; JIT excluded")
+            fn = lambda: ref.run(ENS_B) + (cores,)      # noqa: E731
+            extra = {"numba": ref.version}
+        else:
+            import oracle
+            oracle.build()
+            cores = oracle.use_all_cores()
+            sample = (f"{ENS_B} simulations ({ENS_N} bodies x {ENS_STEPS} steps) per step = one ensemble, C port of the Numba "
+                      f"loop, one thread per simulation, {cores} threads")
+            fn = lambda: cpu_ensemble_sample(ENS_B)      # noqa: E731
+            extra = {"isa": oracle.isa_level()}
     else:
+        import oracle
+        oracle.build()
+        cores = oracle.use_all_cores()
+        kind = "port"
         n = min(args.bodies, 16384)
         sample = f"1 force evaluation at N={n} per step (flat in N), {cores} threads"
         fn = lambda: cpu_single_sample(n)              # noqa: E731
@@ -174,11 +309,12 @@ def run_reference_arm(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * float(np.mean(secs)), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "isa": oracle.isa_level()},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+    if args.workload == "ensemble" and kind == "reference":
+        ref.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,7 +431,9 @@ def bench_ensemble(args, world, rank, local):
     peak_tf = eng.sm_count * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     achieved_tf = inter_step * FLOPS_PER_INTERACTION / k_mean / 1e12
     snap_bytes = B * n_snap * N * 72.0
-    prof = profile_summary().get("ensemble_kernel", {})
+    prof_all = profile_summary()
+    prof = prof_all.get("ensemble_kernel", {})
+    src_now = source_hash()
     probe_tf = eng.fma_peak_tflops("dfma" if dtype == np.float64 else "ffma")
     ops_per_inter = 16 if dtype == np.float64 else 12
     roofline = {
@@ -312,34 +450,58 @@ def bench_ensemble(args, world, rank, local):
                  "frac_of_probe": round(inter_step * ops_per_inter / k_mean / 1e12 / (probe_tf / 2), 4)},
         "kernel_ms": round(k_mean * 1e3, 4),
         "traffic": prof.get("dram_bytes_per_launch"),
+        # the ncu capture behind `traffic` was taken on the sources with this hash; stale when the kernels changed since
+        "traffic_source": prof.get("source"), "traffic_source_hash": prof_all.get("_source_hash"),
+        "traffic_stale": prof_all.get("_source_hash") != src_now, "source_hash": src_now,
         "hbm": {"algorithmic_bytes": snap_bytes, "achieved": round(snap_bytes / k_mean / 1e9, 1),
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(snap_bytes / k_mean / 1e9 / peaks["hbm_gbs"], 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" + (" (fallback)" if peaks.get("_fallback") else " (measured)")},
     }
     cpu = None
+    numba_api_ms = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        # several seconds of wall time on every core (~0.2 s per simulation and thread): 32 simulations per core
-        n_sims = 32 * (os.cpu_count() or 8)
-        v_cpu, s_cpu, cores = cpu_ensemble_sample(n_sims)
-        cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_sims} simulations of the workload's kind ({N} bodies x {T} steps; an ensemble is {B} of them), "
-                         f"one thread per simulation, {s_cpu:.1f} s on {cores} cores"}
-    extra = single_system_extras(eng) if (rank == 0 and not args.no_extras) else None
-    if extra is not None:
-        extra["window_gather_300x401x200_L10"] = window_extras(eng, outs[0][0], outs[0][1])
+        # one whole ensemble (about 30 core-seconds) on the host cores: the reference's own Numba code when
+        # baseline/_ref is here, else the C port of it
+        kind, ref = reference_engine()
+        if kind == "reference":
+            v_cpu, s_cpu = ref.run(B)
+            cores = ref.cores
+            numba_api_ms = ref.api_timings()
+            ref.close()
+            how = f"mp.Pool({cores}) of single-threaded Numba {ref.version} workers (generate_data.py:16-19,143-147), JIT excluded"
+        else:
+            v_cpu, s_cpu, cores = cpu_ensemble_sample(B)
+            how = "C port of the Numba loop, one thread per simulation"
+        cpu = {"value": round(v_cpu, 4), "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{B} simulations ({N} bodies x {T} steps) = one ensemble, {how}, {s_cpu:.1f} s on {cores} cores",
+               "gpu_over_cpu_e2e": round(e2e_value / v_cpu, 1), "gpu_over_cpu_device": round(value / v_cpu, 1),
+               "ratio_note": f"against {cores} host cores"}
+    extra = None
+    if not args.no_extras:
+        extra = {}
+        if rank == 0 and world == 1:
+            extra.update(single_system_extras(eng))
+            extra["window_gather_300x401x200_L10"] = window_extras(eng, outs[0][0], outs[0][1])
+            extra["e2e_device_resident"] = device_resident_extras(eng, x0, v0, m32, dtype, inter_step)
+            extra["simulator_api_N200_400_steps"] = simulator_api_extras(local, numba_api_ms)
+        del outs
+        torch.cuda.empty_cache()
+        extra.update(sharded_extras(eng, world, rank, local))           # every rank takes part
+    if world > 1:
+        # what bounds e2e on several GPUs: the host's aggregate device -> pinned-host bandwidth
+        agg = world * d2h / (e2e_secs / e2e_steps) / 1e9
+        e2e_note = {"aggregate_d2h_GBps": round(agg, 1), "per_gpu_d2h_GBps": round(agg / world, 1)}
+    else:
+        e2e_note = {"d2h_GBps": round(d2h / (e2e_secs / e2e_steps) / 1e9, 1)}
     return {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(1e3 * secs / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"datagen ensemble {B}x{N}x{T} per GPU, fp64 snapshots every step (configs[1])",
-                   "simulations_per_gpu": B, "bodies": N, "sim_steps": T, "save_interval": 1,
-                   "ics": "reference-default (seeded uniform box, shared float32 masses)",
-                   "l2": "each step writes 1.73 GB of fresh snapshot lines (>> 126 MB L2); two output sets alternate",
-                   "parallelism": f"ensemble split over {world} rank(s), no communication"},
+        "config": ensemble_config(),
         "sim_steps_per_s": round(world * args.steps * B * T / secs, 1),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(1e3 * e2e_secs / e2e_steps, 3), "steps": e2e_steps,
-                "api": "hpc.ensemble.simulate_ensemble(host ndarrays) -> host ndarrays"},
+                "api": "hpc.ensemble.simulate_ensemble(host ndarrays) -> host ndarrays", **e2e_note},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
         "also": extra,
     }
@@ -375,6 +537,157 @@ def window_extras(eng, pos_d, vel_d) -> dict:
     return {"ms": round(ms, 4), "samples": int(ins.shape[0]), "algorithmic_bytes": bytes_alg,
             "achieved_GBps": round(gbs, 1), "hbm_peak_GBps": peaks["hbm_gbs"], "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
             "device_fill_of_the_outputs_GBps": round(fill_gbs, 1), "l2": "6.2 GB written per launch (>> 126 MB L2)"}
+
+
+def device_resident_extras(eng, x0, v0, m32, dtype, inter_step) -> dict:
+    """The data-generation pipeline with nothing but the initial conditions crossing PCIe: K3 writes the snapshot
+    stacks to HBM, K5 turns them into the float32 training windows there (what create_training_dataset would write).
+    Host ICs -> device samples, timed end to end with the host clock."""
+    import torch
+    from hpc.checkpoint import sliding_windows_device
+    from hpc.ensemble import simulate_ensemble
+
+    def once():
+        out = simulate_ensemble(x0, v0, m32, dt=1e-3, softening=1e-9, n_steps=ENS_STEPS, save_interval=1, dtype=dtype,
+                                device=eng.device, outputs="device")
+        ins, tgs = sliding_windows_device(out["positions"], out["velocities"], ENS_STEPS + 1, 10)
+        return float(tgs[-1, -1, -1].item())        # device -> host read of the last value produced
+
+    once()
+    torch.cuda.synchronize()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    secs = (time.perf_counter() - t0) / reps
+    return {"value": round(inter_step / secs / 1e9, 2), "unit": UNIT, "ms_per_step": round(secs * 1e3, 3),
+            "h2d_bytes_per_step": int(x0.nbytes + v0.nbytes + m32.nbytes), "d2h_bytes_per_step": int(3 * x0.nbytes + 4),
+            "api": "simulate_ensemble(host ICs, outputs='device') -> sliding_windows_device(L=10): float32 samples in HBM"}
+
+
+def simulator_api_extras(local: int, numba_api_ms) -> dict:
+    """configs[0] (README default: one simulation, N = 200, 400 steps, float64) through the drop-in simulator API,
+    host clock: NBodySimulator.run(400) -> list of 401 states, and the `for ...: sim.step()` loop of the reference's
+    scripts/benchmark_bh_temp.py:24,32 followed by one look at the positions."""
+    import torch
+    from hpc import ics
+    from hpc.nbody import NBodySimulator
+    m32 = ics.shared_masses(ENS_N, 42)
+
+    def make():
+        sim = NBodySimulator(n_particles=ENS_N, box_size=10.0, dt=0.001, seed=42, device=local)
+        sim.masses = m32.copy()
+        sim.accelerations = sim._compute_accelerations()
+        return sim
+
+    make().run(20, verbose=False)
+    best = {"run": 1e9, "run_and_read_all": 1e9, "step_loop": 1e9}
+    for _ in range(5):
+        sim = make()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        states = sim.run(ENS_STEPS, save_interval=1, verbose=False)
+        t1 = time.perf_counter()
+        stacked = np.stack([s["positions"] for s in states])          # what generate_data.py:51 does with the list
+        t2 = time.perf_counter()
+        assert stacked.shape == (ENS_STEPS + 1, ENS_N, 3)
+        best["run"] = min(best["run"], t1 - t0)
+        best["run_and_read_all"] = min(best["run_and_read_all"], t2 - t0)
+        sim = make()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ENS_STEPS):
+            sim.step()
+        x = sim.positions                                              # the one download
+        t1 = time.perf_counter()
+        assert np.isfinite(x).all()
+        best["step_loop"] = min(best["step_loop"], t1 - t0)
+    out = {"run_400_ms": round(best["run"] * 1e3, 3), "run_400_and_stack_all_states_ms": round(best["run_and_read_all"] * 1e3, 3),
+           "step_loop_400_ms": round(best["step_loop"] * 1e3, 3),
+           "step_loop_us_per_step": round(best["step_loop"] * 1e6 / ENS_STEPS, 2)}
+    if numba_api_ms is not None:
+        out["reference_numba_1_thread"] = {"run_400_ms": round(numba_api_ms[0], 2), "step_loop_400_ms": round(numba_api_ms[1], 2)}
+    return out
+
+
+def _time_advance(sysm, steps: int, world: int) -> float:
+    """ms per leapfrog step of sysm.advance(steps): CUDA events on the launch stream, max over ranks."""
+    import torch
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sysm.advance(steps)
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1) / steps, world)
+
+
+def sharded_extras(eng, world: int, rank: int, local: int) -> dict:
+    """BASELINE configs[3] / [4]: one system split by i-slab over the ranks (strong scaling), float32.
+    N = 262,144 at every rank count (3 warm-up + 20 timed steps), N = 1,048,576 at 8 ranks (3 + 5), both exchange
+    modes -- "peer": force + leapfrog + NVLink peer stores + arrival words in ONE kernel (nb_step_peer_*), "nccl": one
+    all-gather per step.  Rank 0 then advances the same system alone by the same steps: the same-run one-GPU step time
+    gives the strong-scaling efficiency, and the final positions / velocities / accelerations must be the same BITS."""
+    import torch
+    from hpc import ics
+    from hpc.sharded import ShardedSystem
+    peaks = measured_peaks()
+    peak_tf = eng.sm_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    out = {}
+    cases = [(262144, 3, 20)]
+    if world >= 8:
+        cases.append((1 << 20, 3, 5))
+    for n, warm, steps in cases:
+        x, v, m = ics.plummer_ic(n, seed=7)
+        eps = 1e-3
+        res = {"bodies": n, "dtype": "f32", "softening": eps, "timed_steps": steps, "warmup_steps": warm, "ranks": world}
+        modes = ["one_gpu"] if world == 1 else ["peer", "nccl"]
+        finals = {}
+        for mode in modes:
+            try:
+                sysm = ShardedSystem(x, v, m, dt=1e-3, softening=eps, dtype=np.float32, device=local, world=world,
+                                     rank=rank, exchange=mode if world > 1 else "auto")
+            except Exception as e:              # noqa: BLE001 -- e.g. symmetric memory unavailable: report, go on
+                res[mode] = {"unavailable": repr(e)[:200]}
+                continue
+            sysm.advance(warm)
+            ms = _time_advance(sysm, steps, world)
+            gi = n * (n - 1.0) / ms / 1e6
+            res[mode] = {"ms_per_step": round(ms, 4), "Ginteractions_per_s": round(gi, 1),
+                         "sim_steps_per_s": round(1e3 / ms, 2), "exchange": getattr(sysm, "exchange", None),
+                         "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / (world * peak_tf), 4),
+                         "peak_tflops": round(world * peak_tf, 2)}
+            if world > 1:
+                finals[mode] = (sysm.positions(), sysm.velocities(), sysm.accelerations())
+            del sysm
+        if world > 1:
+            t1 = None
+            same = {}
+            if rank == 0:
+                one = ShardedSystem(x, v, m, dt=1e-3, softening=eps, dtype=np.float32, device=local)
+                one.advance(warm)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                one.advance(steps)
+                e1.record()
+                e1.synchronize()
+                t1 = e0.elapsed_time(e1) / steps
+                ref = (one.positions(), one.velocities(), one.accelerations())
+                for mode, fin in finals.items():
+                    same[mode] = bool(all(np.array_equal(a, b) for a, b in zip(fin, ref)))
+                del one
+            barrier_sync(world)
+            if rank == 0:
+                res["one_gpu_same_run"] = {"ms_per_step": round(t1, 4),
+                                           "Ginteractions_per_s": round(n * (n - 1.0) / t1 / 1e6, 1)}
+                for mode in modes:
+                    if "ms_per_step" in res.get(mode, {}):
+                        res[mode]["strong_scaling_efficiency"] = round(t1 / (world * res[mode]["ms_per_step"]), 4)
+                        res[mode]["bitwise_equal_to_1gpu"] = same.get(mode)
+        out[f"sharded_N{n}_f32"] = res
+        del x, v, m
+        torch.cuda.empty_cache()
+    return out
 
 
 def single_system_extras(eng) -> dict:
@@ -457,12 +770,9 @@ def bench_single(args, world, rank, local, sharded: bool):
     from hpc.nbody import NBodySimulator
     e2e = None
     if not sharded and rank == 0:
-        np.random.seed(0)
-        sim = NBodySimulator.__new__(NBodySimulator)
-        sim.n_particles, sim.box_size, sim.dt, sim.softening = n, 1.0, 1e-3, eps
-        sim.use_barnes_hut, sim.theta, sim.seed, sim.dtype, sim.device = False, 0.5, None, np.dtype(dtype), local
+        sim = NBodySimulator(n_particles=8, dt=1e-3, softening=eps, seed=0, dtype=dtype, device=local)
+        sim.n_particles = n
         sim.positions, sim.velocities, sim.masses = x.copy(), v.copy(), m.copy()
-        sim.time, sim.step_count, sim.history = 0.0, 0, []
         sim.accelerations = sim._compute_accelerations()
         sim.run(args.sim_steps, save_interval=args.sim_steps, verbose=False)
         t0 = time.perf_counter()

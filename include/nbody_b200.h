@@ -37,6 +37,11 @@ extern "C" {
 #define NB_OK 0
 #define NB_ERR_INVALID 1      /* bad argument (message says which) */
 #define NB_ERR_CUDA 2         /* a CUDA runtime call or launch failed */
+#define NB_ERR_PEER 3         /* sharded mode: another rank never arrived (nb_step_status) */
+
+/* phases recorded in the workspace's error word by nb_step_peer_* (low byte; the lost rank is above it) */
+#define NB_PEER_LOST_BEFORE_FORCE 1   /* wait_seq never reached: the force pass did not run */
+#define NB_PEER_LOST_AFTER_STEP 2     /* NB_STEP_PEER_SYNC: signal_seq of that rank never seen */
 
 /* nb_step_* flags */
 #define NB_STEP_CONTINUE 1    /* after the closing kick, also do the next step's opening kick + drift */
@@ -124,7 +129,10 @@ int nb_step_f32(const float* stream_cur, float* stream_next, float* vel, float* 
  *   signal_seq      published to every rank once this rank's whole slab has been stored (> 0, increasing per step)
  *   NB_STEP_PEER_SYNC in flags: the call additionally waits (on the device, in its last thread block) until every
  *                   rank has published signal_seq here, so the next launch needs no wait_seq
- * i0 must be a multiple of NB_CHUNK_BODIES.  Host arrays of n_ranks pointers; n_ranks <= 16. */
+ * i0 must be a multiple of NB_CHUNK_BODIES.  Host arrays of n_ranks pointers; n_ranks <= 16.
+ * A rank that does not arrive within NB_PEER_TIMEOUT_MS (environment, default 10000) is declared lost: the kernel
+ * records it in the workspace's error word and stops -- this launch and every later one on the workspace leave
+ * without computing -- and nb_step_status() reports it.  A lost peer is never a step from stale positions. */
 int nb_step_peer_f64(const double* stream_cur, void* const* next_peers, void* const* flag_peers, int n_ranks,
                      int my_rank, unsigned wait_seq, unsigned signal_seq, double* vel, double* acc,
                      int n, int i0, int n_i, double dt, double softening, int flags,
@@ -135,6 +143,10 @@ int nb_step_peer_f32(const float* stream_cur, void* const* next_peers, void* con
                      int n, int i0, int n_i, double dt, double softening, int flags,
                      double* snap_pos, double* snap_vel, double* snap_acc,
                      void* workspace, size_t workspace_bytes, nb_stream_t s);
+
+/* Synchronises stream s and reports whether any nb_step_peer_* launch on this workspace lost a peer:
+ * NB_OK, or NB_ERR_PEER with the rank and phase in nb_last_error().  Sticky until the workspace is zeroed. */
+int nb_step_status(const void* workspace, int n, nb_stream_t s);
 
 /* Replaces the loop of NBodySimulator.run, reference src/hpc/nbody.py:237-241, on one GPU:
  * enqueues nb_kick_drift + n_steps x nb_step on stream s.  stream_a holds x_0 on entry; the two

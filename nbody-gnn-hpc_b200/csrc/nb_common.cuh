@@ -46,6 +46,12 @@ inline int check_launch(const char* what) {
     return NB_OK;
 }
 
+// Workspace header of nb_accel_* / nb_step_*: one arrival counter per i-tile of the WHOLE system (smallest tile:
+// 128 bodies), the finished-tiles counter and the error word of the sharded mode.  Sized by n alone.
+static inline size_t ws_header_bytes(int n) {
+    return (((size_t)(n > 0 ? n : 1) / 128 + 3) * sizeof(int) + 255) / 256 * 256;
+}
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

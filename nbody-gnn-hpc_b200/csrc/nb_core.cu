@@ -80,7 +80,7 @@ size_t nb_workspace_bytes(int n, int n_i, int is_f64) {
     bytes = (bytes + 255) / 256 * 256;
     // header: one arrival counter per i-tile of the WHOLE system (smallest tile: 128 bodies), so the layout does not
     // depend on the slab; must be zero before the first launch that uses the workspace -- every launch leaves it zero
-    bytes += (((size_t)(n > 0 ? n : 1) / 128 + 2) * sizeof(int) + 255) / 256 * 256;
+    bytes += nb::ws_header_bytes(n);
     return bytes;
 }
 

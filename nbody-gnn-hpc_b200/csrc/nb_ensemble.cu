@@ -74,7 +74,8 @@ __device__ __forceinline__ void pair_any(float xi, float yi, float zi, float xj,
     r2 = fmaf(dy, dy, r2);
     r2 = fmaf(dz, dz, r2);
     float inv = rsqrt_approx(r2);
-    if (kZeroEps) inv = (r2 > 0.f) ? inv : 0.f;
+    // i == j (r2 == eps2) contributes exactly 0 whatever the magnitudes: G*m*inv^3 may overflow (see nb_force.cu)
+    inv = (r2 > eps2) ? inv : 0.f;
     const float f = (gmj * inv) * (inv * inv);
     ax = fmaf(f, dx, ax);
     ay = fmaf(f, dy, ay);

@@ -19,6 +19,8 @@
 // float32 inner loop: two j bodies per instruction through the packed f32x2 pipe
 // (FADD2/FFMA2/FMUL2), 12 FMA-pipe lane-operations + 1 MUFU.RSQ per interaction.
 // float64 inner loop: pair_f64() in nb_common.cuh, 16 FP64-pipe operations + 1 MUFU.RSQ64H.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "nb_common.cuh"
@@ -70,13 +72,28 @@ struct PeerWait {          // force pass: do not read the stream before every ra
     const uint32_t* flags;  // local array, one word per rank (null: no wait)
     int n_ranks;
     uint32_t seq;
+    unsigned long long timeout_ns;  // a rank that has not arrived after this long is declared lost
+    int* error;             // the workspace's error word (null outside the sharded mode): sticky, checked by the host
 };
 struct PeerTargets {       // finish pass: where the new slab goes and whom to tell
     void* next[kMaxPeers];       // every rank's next-stream buffer (own included)
     uint32_t* flags[kMaxPeers];  // every rank's flag array
     int n_ranks, my_rank;
     uint32_t seq;
+    unsigned long long timeout_ns;
+    int* error;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Error word: phase in the low byte, the rank that never arrived above it.  First failure wins.
+__device__ __forceinline__ void peer_lost(int* error, int phase, int rank) {
+    atomicCAS(error, 0, phase | (rank << 8));
+    __threadfence_system();
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -98,20 +115,30 @@ __device__ __forceinline__ void pdl_prologue() { asm volatile("griddepcontrol.wa
 // step: 31 -> 58 us at N = 4,096 float64, measured.)
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Called by every thread at kernel entry; thread 0 spins (bounded) until all ranks have arrived.
-__device__ __forceinline__ void peer_wait(const PeerWait& w) {
-    if (w.flags == nullptr) return;
-    if (threadIdx.x < w.n_ranks) {  // one polling thread per rank: the loads overlap
-        long long spins = 0;
+// Called by every thread at kernel entry; one thread per rank polls (bounded by timeout_ns) until all ranks have
+// arrived.  Returns false -- and the CTA leaves the kernel without touching anything -- when a rank never arrived
+// (the workspace's error word then says which; nb_step_status reports it) or when an earlier launch on this
+// workspace already failed: a lost peer is an error the host sees, never a step computed from stale positions.
+__device__ __forceinline__ bool peer_wait(const PeerWait& w) {
+    if (w.error == nullptr) return true;  // not the sharded mode
+    int bad = 0;
+    if (threadIdx.x == 0) bad = *reinterpret_cast<volatile int*>(w.error) != 0;
+    if (w.flags != nullptr && threadIdx.x < w.n_ranks) {  // one polling thread per rank: the loads overlap
+        const unsigned long long t0 = global_ns();
         // sequence numbers wrap: compare as signed distance
         while ((int32_t)(ld_acquire_sys(w.flags + threadIdx.x) - w.seq) < 0) {
             __nanosleep(100);
-            if (++spins > (1LL << 26)) break;  // ~10 s: a peer died; do not hang the GPU
+            if (global_ns() - t0 > w.timeout_ns) {
+                peer_lost(w.error, NB_PEER_LOST_BEFORE_FORCE, (int)threadIdx.x);
+                bad = 1;
+                break;
+            }
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(bad)) return false;
     // the stream is read next through the async (TMA) proxy, issued by thread 0
     if (threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -265,10 +292,13 @@ __device__ __forceinline__ void tile_epilogue(const Epilogue<T>& e, const T* par
         st_release_sys(e.peers.flags[threadIdx.x] + e.peers.my_rank, e.peers.seq);
         if (e.flags & NB_STEP_PEER_SYNC) {
             const uint32_t* mine = e.peers.flags[e.peers.my_rank] + threadIdx.x;
-            long long spins = 0;
+            const unsigned long long t0 = global_ns();
             while ((int32_t)(ld_acquire_sys(mine) - e.peers.seq) < 0) {
                 __nanosleep(50);
-                if (++spins > (1LL << 27)) break;  // a peer died; do not hang the GPU
+                if (global_ns() - t0 > e.peers.timeout_ns) {  // that rank died: say so, do not hang the GPU
+                    peer_lost(e.peers.error, NB_PEER_LOST_AFTER_STEP, (int)threadIdx.x);
+                    break;
+                }
             }
         }
     }
@@ -283,7 +313,7 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
     pdl_prologue();
-    peer_wait(wait);
+    if (!peer_wait(wait)) return;
 
     const int seg = blockIdx.y;
     const int j0 = seg * seg_len;
@@ -322,10 +352,12 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
                 float2 inv;
                 inv.x = rsqrt_approx(r2.x);
                 inv.y = rsqrt_approx(r2.y);
-                if (kZeroEps) {
-                    inv.x = (r2.x > 0.f) ? inv.x : 0.f;
-                    inv.y = (r2.y > 0.f) ? inv.y : 0.f;
-                }
+                // The i == j term (and exact overlaps) has r2 == eps2 and must contribute exactly 0 (the reference
+                // skips it, nbody.py:46).  dx = 0 is not enough: with eps = 1e-9, G*m*inv^3 overflows to inf for
+                // G*m > 3.4e11 (any star) and inf * 0 = NaN.  Two ALU-pipe instructions per lane, in issue slots the
+                // FMA-pipe-bound loop leaves free.  (kZeroEps is the same test with eps2 = 0.)
+                inv.x = (r2.x > eps2) ? inv.x : 0.f;
+                inv.y = (r2.y > eps2) ? inv.y : 0.f;
                 const float2 inv2 = __fmul2_rn(inv, inv);
                 float2 f = __fmul2_rn(gj, inv);
                 f = __fmul2_rn(f, inv2);
@@ -361,7 +393,7 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
     __shared__ __align__(128) char ring[kStages * kTileBytes];
     __shared__ __align__(8) uint64_t bars[kStages];
     pdl_prologue();
-    peer_wait(wait);
+    if (!peer_wait(wait)) return;
 
     const int seg = blockIdx.y;
     const int j0 = seg * seg_len;
@@ -508,7 +540,7 @@ template <int kP, int kBlock, bool kZeroEps>
 static void launch_force(const float* stream, const Slab& sl, float eps2, float* partial, const PeerWait& w,
                          const Epilogue<float>& e, cudaStream_t st) {
     dim3 grid(ceil_div(sl.n_i, kP * kBlock), sl.n_seg);
-    launch_pdl(force_f32_kernel<kP, kBlock, kZeroEps>, grid, kBlock, st, stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len,
+    launch_pdl(force_f32_kernel<kP, kBlock, false>, grid  /* one build: the guard is unconditional */, kBlock, st, stream, sl.n_pad, sl.i0, sl.n_i, sl.seg_len,
                eps2, partial, w, e);
 }
 template <int kP, int kBlock, bool kZeroEps>
@@ -521,8 +553,23 @@ static void launch_force(const double* stream, const Slab& sl, double eps2, doub
 
 // Workspace layout: [i-tile arrival counters, sized by n alone][segment partials of this slab].  The header does
 // not depend on the slab, so one workspace serves calls on different slabs of the same system.
-static size_t counter_bytes(int n) { return (((size_t)n / 128 + 2) * sizeof(int) + 255) / 256 * 256; }
+static size_t counter_bytes(int n) { return ws_header_bytes(n); }
 static int* tile_counters(void* ws) { return static_cast<int*>(ws); }
+static int* done_counter(void* ws, int n) { return static_cast<int*>(ws) + ((size_t)n / 128 + 1); }
+static int* error_word(void* ws, int n) { return static_cast<int*>(ws) + ((size_t)n / 128 + 2); }
+
+// How long a kernel of the sharded mode waits for another rank before it declares it lost (NB_PEER_TIMEOUT_MS,
+// default 10 s; read once).
+static unsigned long long peer_timeout_ns() {
+    static unsigned long long ns = 0;
+    if (ns == 0) {
+        const char* e = getenv("NB_PEER_TIMEOUT_MS");
+        double ms = e ? atof(e) : 0.0;
+        if (!(ms > 0.0)) ms = 10000.0;
+        ns = (unsigned long long)(ms * 1e6);
+    }
+    return ns;
+}
 template <typename T>
 static T* partials(void* ws, int n) { return reinterpret_cast<T*>(static_cast<char*>(ws) + counter_bytes(n)); }
 
@@ -539,7 +586,7 @@ static int sm_count() {
 
 template <typename T>
 static int force_pass(const T* stream, const Slab& sl, double softening, T* partial, cudaStream_t st, Epilogue<T> e,
-                      const PeerWait& w = PeerWait{nullptr, 0, 0}) {
+                      const PeerWait& w = PeerWait{nullptr, 0, 0, 0ull, nullptr}) {
     e.n_seg = sl.n_seg;
     const T eps2 = (T)(softening * softening);
     const bool zero = !(eps2 > T(0));
@@ -613,13 +660,15 @@ static int step_peer_impl(const T* cur, void* const* next_peers, void* const* fl
         tg.flags[p] = static_cast<uint32_t*>(flag_peers[p]);
     }
     tg.n_ranks = n_ranks; tg.my_rank = my_rank; tg.seq = signal_seq;
-    PeerWait w{wait_seq ? tg.flags[my_rank] : nullptr, n_ranks, wait_seq};
+    tg.timeout_ns = peer_timeout_ns();
+    tg.error = error_word(ws, n);
+    PeerWait w{wait_seq ? tg.flags[my_rank] : nullptr, n_ranks, wait_seq, tg.timeout_ns, tg.error};
     T* partial = partials<T>(ws, n);
     const double half_dt = 0.5 * dt;
     Epilogue<T> e{};
     e.mode = kEpiStepPeer;
     e.tile_counter = tile_counters(ws);
-    e.done_counter = tile_counters(ws) + (n / 128 + 1);
+    e.done_counter = done_counter(ws, n);
     e.peers = tg;
     e.cur = cur; e.vel = vel; e.acc = acc;
     e.dt = (T)dt; e.half_dt = (T)half_dt; e.flags = flags;
@@ -761,6 +810,20 @@ int nb_step_peer_f32(const float* cur, void* const* next_peers, void* const* fla
                      nb_stream_t s) {
     return nb::step_peer_impl<float>(cur, next_peers, flag_peers, n_ranks, my_rank, wait_seq, signal_seq, vel, acc, n,
                                      i0, n_i, dt, softening, flags, sp, sv, sa, ws, ws_bytes, (cudaStream_t)s);
+}
+
+int nb_step_status(const void* workspace, int n, nb_stream_t s) {
+    NB_REQUIRE(workspace && n > 0, "nb_step_status: bad argument");
+    int word = 0;
+    NB_CUDA_OK(cudaMemcpyAsync(&word, nb::error_word(const_cast<void*>(workspace), n), sizeof(int),
+                               cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    NB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)s));
+    if (word == 0) return NB_OK;
+    const int phase = word & 0xff, rank = word >> 8;
+    nb::set_error("sharded step: rank %d never arrived (%s); the state of this system is no longer valid", rank,
+                  phase == NB_PEER_LOST_BEFORE_FORCE ? "its positions of the previous step were not published in time"
+                                                     : "it did not finish the step in time");
+    return NB_ERR_PEER;
 }
 
 int nb_run_f64(double* stream_a, double* stream_b, double* vel, double* acc, int n, double dt, double softening,

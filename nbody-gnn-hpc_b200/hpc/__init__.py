@@ -6,7 +6,7 @@ to the CUDA engine.  ``CheckpointManager`` is imported lazily because it needs h
 """
 from .nbody import NBodySimulator  # noqa: F401
 
-__all__ = ["NBodySimulator", "CheckpointManager", "BarnesHutTree"]
+__all__ = ["NBodySimulator", "CheckpointManager"]
 
 
 def __getattr__(name):
@@ -16,5 +16,5 @@ def __getattr__(name):
     if name == "BarnesHutTree":
         raise AttributeError(
             "BarnesHutTree is outside this engine's scope: the B200 kernels evaluate the exact direct sum "
-            "at every N (NBodySimulator accepts and ignores use_barnes_hut)")
+            "at every N (NBodySimulator accepts use_barnes_hut, warns once and runs the direct sum)")
     raise AttributeError(name)

@@ -29,6 +29,10 @@ NB_STEP_PEER_SYNC = 4
 # 11.0 / 5.6 at N = 512, 29.5 / 13.9 at N = 768; K2 18.6 / 10.8 at N = 512, 18.9 / 11.1 at N = 768.
 SMALL_SYSTEM_MAX_BODIES = 640
 
+# Host results up to this size are ordinary pageable arrays (copied out of a reusable pinned staging block); larger
+# ones are views of their own pinned block (see Engine.to_host).
+PAGEABLE_RESULT_MAX_BYTES = 64 << 20
+
 
 class EngineUnavailable(RuntimeError):
     """The CUDA engine cannot run here (library not built, or no GPU).  There is no fallback."""
@@ -59,6 +63,7 @@ _SIGNATURES = {
                                _vp, _vp, _vp, _vp, _sz, _vp]),
     "nb_step_peer_f32": (_ci, [_vp, _vp, _vp, _ci, _ci, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci,
                                _vp, _vp, _vp, _vp, _sz, _vp]),
+    "nb_step_status": (_ci, [_vp, _ci, _vp]),
     "nb_run_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_run_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_ensemble_max_bodies": (_ci, []),
@@ -173,17 +178,40 @@ class Engine:
             dev = dev.to(dtype)
         return dev
 
+    def _staging(self, nbytes: int):
+        """The engine's reusable pinned staging block (grown geometrically, never handed out)."""
+        torch = _torch()
+        buf = getattr(self, "_stage_buf", None)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 20, 2 * (buf.numel() if buf is not None else 0)),
+                              dtype=torch.uint8, pin_memory=True)
+            self._stage_buf = buf
+        return buf
+
     def to_host(self, t, pinned: bool = True) -> np.ndarray:
-        """Device tensor -> fresh host float64 ndarray (pinned block from torch's host cache)."""
+        """Device tensor -> fresh host float64 ndarray.
+
+        Up to PAGEABLE_RESULT_MAX_BYTES the copy goes through the engine's reusable pinned staging block into an
+        ordinary (pageable) array, so retained results do not keep memory page-locked.  Larger results (the 1.7 GB
+        snapshot stacks of an ensemble) are handed out as views of their own pinned block: a second pass over them
+        on the host would cost several times the whole GPU run; such an array keeps its block page-locked for as
+        long as it is alive (np.array(x) makes a pageable copy)."""
         torch = _torch()
         if t.dtype != torch.float64:
             t = t.to(torch.float64)
-        if pinned and t.numel() * 8 >= (1 << 16):
-            host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
-            host.copy_(t, non_blocking=True)
+        t = t.contiguous()
+        nbytes = t.numel() * 8
+        if not pinned or nbytes < (1 << 12):
+            return t.cpu().numpy()
+        if nbytes <= PAGEABLE_RESULT_MAX_BYTES:
+            stage = self._staging(nbytes)[:nbytes].view(torch.float64).view(t.shape)
+            stage.copy_(t, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            return host.numpy()
-        return t.cpu().numpy()
+            return stage.numpy().copy()
+        host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def _masses_dev(self, masses):
         m = np.asarray(masses)
@@ -285,6 +313,10 @@ class Engine:
             self._p(snap_vel), self._p(snap_acc), self._p(ws[0]), ws[1], self._stream()))
         self.launches += 1  # force + leapfrog + peer stores + arrival words: one kernel
 
+    def step_status(self, ws, n: int) -> None:
+        """Synchronise and raise if a nb_step_peer_* launch on this workspace lost a peer (NB_ERR_PEER)."""
+        self._check(self.lib.nb_step_status(self._p(ws[0]), int(n), self._stream()))
+
     # ---- host-level operations (ndarrays in, ndarrays out; the reference's call shapes) ----------
     def accelerations(self, positions, masses, softening: float, dtype=np.float64) -> np.ndarray:
         """compute_accelerations_direct (reference nbody.py:22-66) -> new (N,3) float64 ndarray."""
@@ -298,50 +330,26 @@ class Engine:
             acc = self.accel_slab(stream, n, 0, n, softening)
             return self.to_host(acc)
 
+    def resident(self, positions, velocities, accelerations, masses, dt: float, softening: float,
+                 dtype=np.float64) -> "ResidentSystem":
+        """Upload one system's (x, v, a, m) and keep it in device memory: what NBodySimulator holds between
+        step()/run() calls."""
+        return ResidentSystem(self, positions, velocities, accelerations, masses, dt, softening, dtype)
+
     def run(self, positions, velocities, accelerations, masses, dt: float, softening: float, n_steps: int,
             save_interval: int = 1, dtype=np.float64, snapshots: bool = True) -> dict:
-        """The loop of NBodySimulator.run (reference nbody.py:232-248) from an explicit (x, v, a).
+        """The loop of NBodySimulator.run (reference nbody.py:232-248) from an explicit (x, v, a), one shot.
 
         Returns snapshot stacks (n_snap, N, 3) float64 -- row 0 is the entry state -- and the final
         synchronised state.
         """
-        torch = _torch()
-        pos = np.ascontiguousarray(positions, dtype=np.float64)
-        n = pos.shape[0]
-        if n <= SMALL_SYSTEM_MAX_BODIES:
-            out = self.ensemble(pos[None], np.asarray(velocities, dtype=np.float64)[None], masses, dt, softening,
-                                n_steps, save_interval, dtype=dtype, a0=np.asarray(accelerations, dtype=np.float64)[None],
-                                snapshots=snapshots)
-            res = {"final_positions": out["final_positions"][0], "final_velocities": out["final_velocities"][0],
-                   "final_accelerations": out["final_accelerations"][0]}
-            if snapshots:
-                res.update(positions=out["positions"][0], velocities=out["velocities"][0],
-                           accelerations=out["accelerations"][0])
-            return res
-        sfx = self._suffix(dtype)
-        td = self._tdtype(dtype)
-        n_snap = 1 + n_steps // save_interval
-        with torch.cuda.device(self.device):
-            pos_d = self.to_device(pos)
-            m_d, f32 = self._masses_dev(masses)
-            sa = self.pack(pos_d, m_d, f32, n, dtype)
-            sb = sa.clone()
-            vel = self.to_device(np.asarray(velocities, dtype=np.float64), td)
-            acc = self.to_device(np.asarray(accelerations, dtype=np.float64), td)
-            ws = self.workspace(n, n, dtype)
-            if snapshots:
-                sp = torch.empty((n_snap, n, 3), dtype=torch.float64, device=self.device)
-                sv = torch.empty_like(sp)
-                sc = torch.empty_like(sp)
-            else:
-                sp = sv = sc = None
-            in_a = self.run_device(sa, sb, vel, acc, n, dt, softening, n_steps, save_interval, sp, sv, sc, ws)
-            final_pos = self.unpack(sa if in_a else sb, n)
-            res = {"final_positions": self.to_host(final_pos), "final_velocities": self.to_host(vel),
-                   "final_accelerations": self.to_host(acc)}
-            if snapshots:
-                res.update(positions=self.to_host(sp), velocities=self.to_host(sv), accelerations=self.to_host(sc))
-            return res
+        rs = self.resident(positions, velocities, accelerations, masses, dt, softening, dtype)
+        out = rs.advance(n_steps, save_interval, snapshots=snapshots)
+        fp, fv, fa = rs.download()
+        res = {"final_positions": fp, "final_velocities": fv, "final_accelerations": fa}
+        if snapshots:
+            res.update(out)
+        return res
 
     def run_device(self, stream_a, stream_b, vel, acc, n: int, dt: float, softening: float, n_steps: int,
                    save_interval: int, snap_pos, snap_vel, snap_acc, ws) -> bool:
@@ -522,6 +530,89 @@ class Engine:
                                            float(softening), self._p(ku), self._p(ws), nbytes, self._stream()))
         self.launches += 2
         return ku
+
+
+class ResidentSystem:
+    """One system's state in device memory between calls: NBodySimulator.step()/run() (reference nbody.py:202-248)
+    advance it where it lies; nothing crosses PCIe until the caller looks at the state.
+
+    N <= SMALL_SYSTEM_MAX_BODIES: (x, v, a) float64 in API layout, advanced by the one-launch kernel K3 (a cluster of
+    8 CTAs per system); larger: the two position streams plus (v, a) in the kernel dtype, advanced by one fused
+    force + leapfrog launch per step (K2), all steps of a call enqueued by one C call."""
+
+    def __init__(self, eng: Engine, positions, velocities, accelerations, masses, dt, softening, dtype):
+        torch = _torch()
+        self.eng, self.dt, self.softening, self.dtype = eng, float(dt), float(softening), np.dtype(dtype)
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
+        self.n = n = pos.shape[0]
+        self.small = n <= SMALL_SYSTEM_MAX_BODIES
+        xva = np.stack([pos, np.asarray(velocities, dtype=np.float64), np.asarray(accelerations, dtype=np.float64)])
+        with torch.cuda.device(eng.device):
+            self.m_d, self.m_f32 = eng._masses_dev(masses)
+            xva_d = eng.to_device(xva)                                  # ONE host -> device copy of the state
+            if self.small:
+                self.xva = xva_d.view(3, 1, n, 3)
+                nbytes = int(eng.lib.nb_ensemble_workspace_bytes(1))
+                self.ws = (torch.empty(nbytes, dtype=torch.uint8, device=eng.device), nbytes)
+            else:
+                td = eng._tdtype(self.dtype)
+                self.cur = eng.pack(xva_d[0], self.m_d, self.m_f32, n, self.dtype)
+                self.nxt = self.cur.clone()
+                self.vel = xva_d[1].to(td) if td != torch.float64 else xva_d[1].clone()
+                self.acc = xva_d[2].to(td) if td != torch.float64 else xva_d[2].clone()
+                self.ws = eng.workspace(n, n, self.dtype)
+
+    def advance(self, n_steps: int, save_interval: int = 1, snapshots: bool = False):
+        """n_steps kick-drift-kick steps on the device.  snapshots=True: returns {'positions','velocities',
+        'accelerations'}: host stacks (1 + n_steps // save_interval, N, 3) float64, row 0 = the state on entry
+        (one device -> host copy for all three)."""
+        torch = _torch()
+        eng, n = self.eng, self.n
+        n_snap = 1 + n_steps // save_interval
+        with torch.cuda.device(eng.device):
+            snaps = torch.empty((3, n_snap, n, 3), dtype=torch.float64, device=eng.device) if snapshots else None
+            if self.small:
+                ox, ov, oa = ((snaps[0].view(1, n_snap, n, 3), snaps[1].view(1, n_snap, n, 3),
+                               snaps[2].view(1, n_snap, n, 3)) if snapshots else (None, None, None))
+                eng.ensemble_device(self.xva[0], self.xva[1], self.xva[2], self.m_d, self.m_f32, 0, 1, n, self.dt,
+                                    self.softening, n_steps, save_interval, self.dtype, compute_a0=False,
+                                    write_initial=snapshots, out_x=ox, out_v=ov, out_a=oa,
+                                    n_snap_total=n_snap if snapshots else 0, snap_offset=0, ws=self.ws)
+            else:
+                sp, sv, sa = (snaps[0], snaps[1], snaps[2]) if snapshots else (None, None, None)
+                in_a = eng.run_device(self.cur, self.nxt, self.vel, self.acc, n, self.dt, self.softening, n_steps,
+                                      save_interval, sp, sv, sa, self.ws)
+                if not in_a:
+                    self.cur, self.nxt = self.nxt, self.cur
+            if not snapshots:
+                return None
+            host = eng.to_host(snaps)
+        return {"positions": host[0], "velocities": host[1], "accelerations": host[2]}
+
+    def download(self):
+        """(positions, velocities, accelerations): fresh host float64 (N,3) arrays of the current state."""
+        torch = _torch()
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            if self.small:
+                h = eng.to_host(self.xva.view(3, self.n, 3))
+            else:
+                h = eng.to_host(torch.stack([eng.unpack(self.cur, self.n), self.vel.to(torch.float64),
+                                             self.acc.to(torch.float64)]))
+        return h[0], h[1], h[2]
+
+    def energy(self):
+        """(K, U, K+U) of the resident state (K4, float64)."""
+        torch = _torch()
+        eng, n = self.eng, self.n
+        with torch.cuda.device(eng.device):
+            if self.small:
+                pos_d, vel_d = self.xva[0, 0], self.xva[1, 0]
+            else:
+                pos_d, vel_d = eng.unpack(self.cur, n), self.vel.to(torch.float64)
+            ku = eng.energy_slab(pos_d, vel_d, self.m_d, self.m_f32, n, 0, n, self.softening)
+            k, u = (float(t) for t in ku.cpu())
+        return k, u, k + u
 
 
 _engines: dict = {}

@@ -30,7 +30,7 @@ def simulate_ensemble(positions, velocities, masses, dt: float = 1e-3, softening
     """
     if outputs not in ("host", "device"):
         raise ValueError("outputs must be 'host' or 'device'")
-    eng = nbody._backend_override or nbody._cuda.get_engine(device)
+    eng = nbody._cuda.get_engine(device)
     kw = {"outputs": outputs} if outputs != "host" else {}
     out = eng.ensemble(positions, velocities, masses, float(dt), float(softening), int(n_steps), int(save_interval),
                        dtype=nbody._engine_dtype(dtype), a0=accelerations, snapshots=snapshots, **kw)

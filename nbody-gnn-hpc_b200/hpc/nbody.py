@@ -11,14 +11,19 @@ The arithmetic runs in hand-written sm_100a CUDA kernels behind a C ABI (``inclu
 bound in ``hpc/_cuda.py``).  There is no CPU fallback: without the built library or without a
 CUDA device every force evaluation raises ``EngineUnavailable``.
 
-Host NumPy arrays stay the source of truth between calls, exactly as in the reference: callers
-assign ``sim.masses`` / ``sim.positions`` (or write into slices of them) and then call
-``_compute_accelerations()`` or ``run()``.  ``run()`` uploads the state once, advances all steps on
-the device with snapshots written by the kernels, and downloads the stacked snapshots once.
+Where the state lives.  ``positions``, ``velocities``, ``accelerations`` and ``masses`` are ordinary NumPy
+arrays whenever the caller looks at them or assigns them -- exactly the reference's attributes -- but between
+``step()`` / ``run()`` calls the state stays in device memory: it is uploaded when the caller has assigned or may
+have written the host arrays since the last upload, and downloaded when the caller next reads an attribute (or,
+after every call, while the caller still holds a reference to the position / velocity arrays, so that such aliases
+see the in-place updates of reference nbody.py:205-214).  ``for _ in range(k): sim.step()`` therefore costs k kernel
+launches and no copies; ``run()`` returns a list whose state dictionaries are built when they are first accessed.
 """
 from __future__ import annotations
 
 import os
+import sys
+import warnings
 from typing import Optional, Tuple
 
 import numpy as np
@@ -29,20 +34,7 @@ from . import _cuda
 G = 6.67430e-11
 SOFTENING = 1e-9
 
-_backend_override = None
-
-
-def _backend():
-    """The object that executes the hot path: the CUDA engine (tests may install a stand-in)."""
-    if _backend_override is not None:
-        return _backend_override
-    return _cuda.get_engine()
-
-
-def _set_backend_for_tests(backend) -> None:
-    """Install a stand-in backend (tests of the host-side bookkeeping on machines without a GPU)."""
-    global _backend_override
-    _backend_override = backend
+_bh_warned = False
 
 
 def _engine_dtype(dtype) -> np.dtype:
@@ -69,13 +61,14 @@ def compute_accelerations_direct(positions: np.ndarray, masses: np.ndarray,
         raise ValueError(f"masses must have shape ({positions.shape[0]},), got {masses.shape}")
     if positions.shape[0] == 0:
         return np.zeros((0, 3))
-    return _backend().accelerations(positions, masses, float(softening), _engine_dtype(dtype))
+    return _cuda.get_engine().accelerations(positions, masses, float(softening), _engine_dtype(dtype))
 
 
 def compute_total_energy(positions: np.ndarray, velocities: np.ndarray, masses: np.ndarray,
                          softening: float = SOFTENING) -> Tuple[float, float, float]:
     """(kinetic, potential, total) energy (reference nbody.py:101-130), float64 on the device."""
-    return _backend().energy(np.asarray(positions), np.asarray(velocities), np.asarray(masses), float(softening))
+    return _cuda.get_engine().energy(np.asarray(positions), np.asarray(velocities), np.asarray(masses),
+                                     float(softening))
 
 
 def leapfrog_step(positions: np.ndarray, velocities: np.ndarray, accelerations: np.ndarray,
@@ -90,12 +83,127 @@ def leapfrog_step(positions: np.ndarray, velocities: np.ndarray, accelerations: 
     return new_positions, velocities_half, accelerations
 
 
+def _refs(holder: dict, name: str) -> int:
+    return sys.getrefcount(holder[name])
+
+
+# what _refs reports for an array nobody but its holder refers to (calibrated, not assumed)
+_UNSHARED_REFS = _refs({"x": np.zeros(1)}, "x")
+
+
+class StateList(list):
+    """The list ``NBodySimulator.run`` returns (reference nbody.py:232-248): one state dictionary per saved step,
+    built when it is first accessed.  The snapshots arrive from the device as three stacked arrays; a state's
+    'positions' / 'velocities' / 'accelerations' are the rows of those stacks (disjoint, writable, owned by this
+    list alone -- independent of each other and of the simulator, like the reference's copies).  Behaves as the
+    plain list it subclasses in every other respect."""
+
+    def __init__(self, first: dict, masses: np.ndarray):
+        super().__init__([first])
+        self._masses = masses
+        self._lazy = []          # (index in the list, stacks, row, time, step) not yet materialised
+
+    def _append_rows(self, stacks: dict, rows, times, steps) -> None:
+        for r, t, k in zip(rows, times, steps):
+            self._lazy.append((len(self), stacks, r, t, k))
+            super().append(None)
+
+    def _materialise(self) -> None:
+        if self._lazy:
+            for idx, stacks, r, t, k in self._lazy:
+                super().__setitem__(idx, {
+                    'positions': stacks['positions'][r],
+                    'velocities': stacks['velocities'][r],
+                    'accelerations': stacks['accelerations'][r],
+                    'masses': self._masses.copy(),
+                    'time': t,
+                    'step': k,
+                })
+            self._lazy = []
+
+    def __getitem__(self, i):
+        self._materialise()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._materialise()
+        return super().__iter__()
+
+    def __reversed__(self):
+        self._materialise()
+        return super().__reversed__()
+
+    def __contains__(self, x):
+        self._materialise()
+        return super().__contains__(x)
+
+    def __eq__(self, other):
+        self._materialise()
+        return super().__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._materialise()
+        return super().__repr__()
+
+    def __add__(self, other):
+        self._materialise()
+        return list(super().__iter__()) + list(other)
+
+    def __reduce__(self):
+        self._materialise()
+        return (list, (list(super().__iter__()),))
+
+    def copy(self):
+        self._materialise()
+        return list(super().__iter__())
+
+    def index(self, *a):
+        self._materialise()
+        return super().index(*a)
+
+    def count(self, x):
+        self._materialise()
+        return super().count(x)
+
+    def pop(self, *a):
+        self._materialise()
+        return super().pop(*a)
+
+    def sort(self, **kw):
+        self._materialise()
+        return super().sort(**kw)
+
+    def reverse(self):
+        self._materialise()
+        return super().reverse()
+
+    def insert(self, *a):
+        self._materialise()
+        return super().insert(*a)
+
+    def remove(self, x):
+        self._materialise()
+        return super().remove(x)
+
+    def __setitem__(self, i, v):
+        self._materialise()
+        return super().__setitem__(i, v)
+
+    def __delitem__(self, i):
+        self._materialise()
+        return super().__delitem__(i)
+
+
 class NBodySimulator:
     """High-performance N-body gravitational simulator (reference nbody.py:133-337).
 
     Extra keyword-only options: ``dtype`` ('float64' default, or 'float32' for the fast kernels;
     env NBODY_DTYPE overrides the default) and ``device`` (CUDA device index).
     """
+
+    _ARRAYS = ("positions", "velocities", "accelerations")
 
     def __init__(self,
                  n_particles: int = 1000,
@@ -107,17 +215,30 @@ class NBodySimulator:
                  theta: float = 0.5,
                  seed: Optional[int] = None,
                  *, dtype=None, device=None):
+        global _bh_warned
         self.n_particles = n_particles
         self.box_size = box_size
         self.dt = dt
         self.softening = softening
-        # The flag is kept for call compatibility (generate_data.py:41 sets it for N > 500); the
-        # engine always evaluates the exact direct sum, which the tree code approximates.
+        # The flag is kept for call compatibility (generate_data.py:41 sets it for N > 500; reference
+        # nbody.py:193-198 then walks a theta = 0.5 tree).  This engine evaluates the exact direct sum the tree
+        # approximates -- O(N^2), but 2.7e12 interactions/s -- and says so once per process.
         self.use_barnes_hut = use_barnes_hut
+        if use_barnes_hut and not _bh_warned:
+            _bh_warned = True
+            warnings.warn(
+                "use_barnes_hut=True: the B200 engine evaluates the exact direct sum at every N (theta is ignored), "
+                "so trajectories are the direct-sum ones, not the reference's theta=0.5 tree approximation "
+                "(which also ignores the simulator's softening, reference nbody.py:197-198)", stacklevel=2)
         self.theta = theta
         self.seed = seed
         self.dtype = _engine_dtype(dtype)
         self.device = device
+
+        self._host = {}            # the host arrays the caller sees
+        self._resident = None      # _cuda.ResidentSystem holding the state on the device, or None
+        self._host_stale = False   # the device state is newer than the host arrays
+        self._host_touched = True  # the caller assigned, or may have written, host arrays since the last upload
 
         # same draws, same order, same (global) generator as reference nbody.py:175-181
         if seed is not None:
@@ -132,31 +253,83 @@ class NBodySimulator:
         self.step_count = 0
         self.history = []
 
+    # ---- state attributes: host arrays on demand, device memory in between -------------------------------------
+    def _read(self, name: str) -> np.ndarray:
+        """Attribute read by the CALLER: the host array, refreshed from the device if it is stale.  The caller may
+        write through the returned reference (the reference's factories do, nbody.py:294-300), so the host copy
+        counts as touched."""
+        self._sync_host()
+        self._host_touched = True
+        return self._host[name]
+
+    def _write(self, name: str, value) -> None:
+        if self._host_stale:
+            self._sync_host()              # the other attributes must be current before the host becomes the truth
+        self._host[name] = value
+        self._host_touched = True
+
+    positions = property(lambda self: self._read("positions"), lambda self, v: self._write("positions", v))
+    velocities = property(lambda self: self._read("velocities"), lambda self, v: self._write("velocities", v))
+    accelerations = property(lambda self: self._read("accelerations"), lambda self, v: self._write("accelerations", v))
+    masses = property(lambda self: self._read("masses"), lambda self, v: self._write("masses", v))
+
+    def _sync_host(self) -> None:
+        """Bring the host arrays up to date: positions and velocities IN PLACE (the reference's += updates,
+        nbody.py:205-214, keep aliases valid), accelerations rebound (nbody.py:211)."""
+        if not self._host_stale:
+            return
+        pos, vel, acc = self._resident.download()
+        h = self._host
+        for name, new in (("positions", pos), ("velocities", vel)):
+            old = h.get(name)
+            if isinstance(old, np.ndarray) and old.shape == new.shape and old.dtype == new.dtype and old.flags.writeable:
+                old[...] = new
+            else:
+                h[name] = new
+        h["accelerations"] = acc
+        self._host_stale = False
+
+    def _aliased(self) -> bool:
+        """Does anybody but this object hold a reference to the position / velocity host arrays (or a view of
+        them)?  Such an alias must see every step's in-place update, and may be written through at any time."""
+        h = self._host
+        return _refs(h, "positions") > _UNSHARED_REFS or _refs(h, "velocities") > _UNSHARED_REFS
+
+    def _device_state(self):
+        """The resident device state, (re)built from the host arrays when the caller has touched them."""
+        if self._resident is None or self._host_touched or self._aliased():
+            self._sync_host()
+            h = self._host
+            self._resident = self._engine().resident(h["positions"], h["velocities"], h["accelerations"], h["masses"],
+                                                     float(self.dt), float(self.softening), self.dtype)
+            self._host_touched = False
+        else:
+            self._resident.dt, self._resident.softening = float(self.dt), float(self.softening)
+        return self._resident
+
     # ------------------------------------------------------------------------------------------
     def _engine(self):
-        if _backend_override is not None:
-            return _backend_override
         return _cuda.get_engine(self.device)
 
     def _compute_accelerations(self) -> np.ndarray:
         """Accelerations of the current host state (reference nbody.py:193-200)."""
         if self.n_particles == 0:
             return np.zeros((0, 3))
-        return self._engine().accelerations(self.positions, self.masses, float(self.softening), self.dtype)
+        self._sync_host()
+        h = self._host
+        return self._engine().accelerations(h["positions"], h["masses"], float(self.softening), self.dtype)
 
     def _advance(self, n_steps: int, save_interval: int, snapshots: bool) -> Optional[dict]:
-        """Upload (x, v, a), advance n_steps on the device, download; updates the live state."""
-        out = self._engine().run(self.positions, self.velocities, self.accelerations, self.masses, float(self.dt),
-                                 float(self.softening), int(n_steps), int(save_interval), dtype=self.dtype,
-                                 snapshots=snapshots)
-        # in-place, as the reference's  +=  updates are (aliases of the arrays stay valid)
-        self.positions[...] = out["final_positions"]
-        self.velocities[...] = out["final_velocities"]
-        self.accelerations = np.array(out["final_accelerations"])  # rebinding, reference nbody.py:211
+        """n_steps on the device; the live state stays there (host arrays refreshed only while aliased)."""
+        rs = self._device_state()
+        out = rs.advance(int(n_steps), int(save_interval), snapshots=snapshots)
+        self._host_stale = True
         for _ in range(n_steps):
             self.time += self.dt          # a running float sum, reference nbody.py:217
         self.step_count += n_steps
-        return out if snapshots else None
+        if self._aliased():
+            self._sync_host()             # in place, as the reference's  +=  updates are
+        return out
 
     def step(self) -> None:
         """Advance the simulation by one kick-drift-kick step (reference nbody.py:202-218)."""
@@ -170,12 +343,12 @@ class NBodySimulator:
         into that many device segments.
         """
         s0 = self.step_count
-        states = [self.get_state()]
+        masses = self._host["masses"]
+        states = StateList(self.get_state(), masses)
         if n_steps <= 0:
             self.history = states
             return states
         report = max(1, n_steps // 10)
-        masses = self.masses
         # times[k]: the float the reference holds after k additions of dt (nbody.py:217)
         times = [self.time]
         for _ in range(n_steps):
@@ -187,18 +360,16 @@ class NBodySimulator:
             phase = done % save_interval
             if phase:  # a report point fell between two save points: walk to the next save point first
                 lead = min(save_interval - phase, seg)
-                self._advance(lead, 1, snapshots=False)
+                out = self._advance(lead, lead, snapshots=True)
                 done += lead
                 seg -= lead
                 if done % save_interval == 0:
-                    states.append(self._state_from(self.positions, self.velocities, self.accelerations, masses,
-                                                   times[done], s0 + done))
+                    states._append_rows(out, [1], [times[done]], [s0 + done])
             if seg > 0:
                 out = self._advance(seg, save_interval, snapshots=True)
-                for r in range(1, seg // save_interval + 1):
-                    k = done + r * save_interval
-                    states.append(self._state_from(out["positions"][r], out["velocities"][r],
-                                                   out["accelerations"][r], masses, times[k], s0 + k))
+                rows = range(1, seg // save_interval + 1)
+                ks = [done + r * save_interval for r in rows]
+                states._append_rows(out, rows, [times[k] for k in ks], [s0 + k for k in ks])
                 done += seg
             if verbose and done % report == 0:
                 energy = self.get_energy()
@@ -206,41 +377,36 @@ class NBodySimulator:
         self.history = states
         return states
 
-    @staticmethod
-    def _state_from(pos, vel, acc, masses, time, step) -> dict:
-        return {
-            'positions': np.array(pos),
-            'velocities': np.array(vel),
-            'accelerations': np.array(acc),
-            'masses': masses.copy(),
-            'time': time,
-            'step': step,
-        }
-
     def get_state(self) -> dict:
         """Current simulation state as a dictionary of copies (reference nbody.py:250-259)."""
+        self._sync_host()
+        h = self._host
         return {
-            'positions': self.positions.copy(),
-            'velocities': self.velocities.copy(),
-            'accelerations': self.accelerations.copy(),
-            'masses': self.masses.copy(),
+            'positions': h["positions"].copy(),
+            'velocities': h["velocities"].copy(),
+            'accelerations': h["accelerations"].copy(),
+            'masses': h["masses"].copy(),
             'time': self.time,
             'step': self.step_count
         }
 
     def set_state(self, state: dict) -> None:
         """Restore the simulation from a state dictionary (reference nbody.py:261-268)."""
+        self._host_stale = False           # whatever the device holds is superseded
         self.positions = state['positions'].copy()
         self.velocities = state['velocities'].copy()
         self.accelerations = state['accelerations'].copy()
         self.masses = state['masses'].copy()
         self.time = state['time']
         self.step_count = state['step']
-        self.n_particles = self.positions.shape[0]
+        self.n_particles = self._host["positions"].shape[0]
 
     def get_energy(self) -> Tuple[float, float, float]:
         """Current (kinetic, potential, total) energy (reference nbody.py:270-273)."""
-        return self._engine().energy(self.positions, self.velocities, self.masses, float(self.softening))
+        if self._host_stale and not self._host_touched:
+            return self._resident.energy()          # the state is on the device: evaluate it there
+        h = self._host
+        return self._engine().energy(h["positions"], h["velocities"], h["masses"], float(self.softening))
 
     # ------------------------------------------------------------------------------------------
     @classmethod

@@ -16,9 +16,23 @@ from __future__ import annotations
 
 import numpy as np
 
+import contextlib
+import functools
+
 from . import _cuda
 
-CHUNK = 32  # NB_CHUNK_BODIES: slab boundaries are multiples of it
+CHUNK = 32
+
+
+def _on_own_device(method):
+    """Run a ShardedSystem method with the engine's device current: the C side launches on the current CUDA
+    device while the stream comes from the engine's device, so the two must agree whatever the caller's
+    current device is."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self._device_guard():
+            return method(self, *args, **kwargs)
+    return wrapper  # NB_CHUNK_BODIES: slab boundaries are multiples of it
 
 
 def slab_bounds(n: int, world: int):
@@ -43,10 +57,25 @@ class ShardedSystem:
     """Device-resident state of one system, advanced slab-wise.  world == 1 is the plain one-GPU case."""
 
     def __init__(self, positions, velocities, masses, dt: float, softening: float, dtype=np.float64, device=None,
-                 world: int = 1, rank: int = 0, group=None, engine=None, accelerations=None, exchange: str = "auto"):
+                 world: int = 1, rank: int = 0, group=None, engine=None, accelerations=None, exchange: str = "auto",
+                 check_peers: bool = True):
         import torch
         self.torch = torch
         self.eng = engine if engine is not None else _cuda.get_engine(device)
+        self.check_peers = bool(check_peers)
+        with self._device_guard():
+            self._init(positions, velocities, masses, dt, softening, dtype, world, rank, group, engine,
+                       accelerations, exchange)
+
+    def _device_guard(self):
+        dev = getattr(self.eng, "device", None)
+        if dev is not None and getattr(dev, "type", "cpu") == "cuda":
+            return self.torch.cuda.device(dev)
+        return contextlib.nullcontext()
+
+    def _init(self, positions, velocities, masses, dt, softening, dtype, world, rank, group, engine, accelerations,
+              exchange):
+        torch = self.torch
         self.n = int(np.asarray(positions).shape[0])
         self.dt, self.softening = float(dt), float(softening)
         self.dtype = np.dtype(dtype)
@@ -126,6 +155,7 @@ class ShardedSystem:
             _all_gather_inplace(self.dist, stream, self.slab * 4, self.rank, self.group)
 
     # -- stepping -------------------------------------------------------------------------------
+    @_on_own_device
     def advance(self, n_steps: int, snap_pos=None, snap_vel=None, snap_acc=None, save_interval: int = 1):
         """n_steps kick-drift-kick steps.  snap_*: optional device tensors (n_snap, N, 3) float64; each
         rank fills the rows of its own slab for the saved steps (row s = state after s*save_interval)."""
@@ -174,8 +204,12 @@ class ShardedSystem:
             if save:
                 snap += 1
         self.steps_done += n_steps
+        if self._peer is not None and self.check_peers:
+            # a rank that never arrived is an error, not a step from stale positions (synchronises this stream)
+            eng.step_status(self.ws, self.n)
 
     # -- results --------------------------------------------------------------------------------
+    @_on_own_device
     def positions(self) -> np.ndarray:
         """Full (N,3) float64 positions (every rank holds them)."""
         return self.eng.unpack(self.cur, self.n).cpu().numpy()
@@ -190,12 +224,15 @@ class ShardedSystem:
         _all_gather_inplace(self.dist, full.view(-1), self.slab * 3, self.rank, self.group)
         return full[:self.n].cpu().numpy()
 
+    @_on_own_device
     def velocities(self) -> np.ndarray:
         return self._gather_rows(self.vel)
 
+    @_on_own_device
     def accelerations(self) -> np.ndarray:
         return self._gather_rows(self.acc)
 
+    @_on_own_device
     def energy(self):
         """(K, U, K+U): every rank sums its slab (K4), one all-reduce of two doubles."""
         torch = self.torch

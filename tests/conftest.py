@@ -18,6 +18,11 @@ for p in (str(ROOT), str(PKG)):
 
 GOLDEN = ROOT / "tests" / "golden"
 
+# sharded mode: how long a kernel waits for another rank before it reports it lost (read once by the library);
+# short, so that the lost-peer test takes seconds
+import os  # noqa: E402
+os.environ.setdefault("NB_PEER_TIMEOUT_MS", "1500")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

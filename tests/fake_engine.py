@@ -11,6 +11,32 @@ NB_STEP_CONTINUE, NB_STEP_SNAPSHOT = 1, 2
 G = 6.67430e-11
 
 
+class FakeResident:
+    """Stand-in for hpc._cuda.ResidentSystem: the state lives here between calls, the oracle advances it."""
+
+    def __init__(self, eng, positions, velocities, accelerations, masses, dt, softening):
+        self.eng, self.dt, self.softening = eng, dt, softening
+        self.x = np.array(positions, dtype=np.float64)
+        self.v = np.array(velocities, dtype=np.float64)
+        self.a = np.array(accelerations, dtype=np.float64)
+        self.m = np.array(masses)
+
+    def advance(self, n_steps, save_interval=1, snapshots=False):
+        self.eng.calls.append(("run", n_steps, save_interval, snapshots))
+        out = oracle.run(self.x, self.v, self.a, self.m, self.dt, self.softening, n_steps, save_interval)
+        self.x, self.v, self.a = out["final_positions"], out["final_velocities"], out["final_accelerations"]
+        if snapshots:
+            return {k: out[k] for k in ("positions", "velocities", "accelerations")}
+        return None
+
+    def download(self):
+        self.eng.calls.append(("download",))
+        return self.x.copy(), self.v.copy(), self.a.copy()
+
+    def energy(self):
+        return oracle.total_energy(self.x, self.v, self.m, self.softening)
+
+
 class FakeEngine:
     device = torch.device("cpu")
     sm_count = 148
@@ -35,6 +61,10 @@ class FakeEngine:
         if snapshots:
             res.update(positions=out["positions"], velocities=out["velocities"], accelerations=out["accelerations"])
         return res
+
+    def resident(self, positions, velocities, accelerations, masses, dt, softening, dtype=np.float64):
+        self.calls.append(("resident", np.asarray(positions).shape[0]))
+        return FakeResident(self, positions, velocities, accelerations, masses, dt, softening)
 
     def ensemble(self, x0, v0, masses, dt, softening, n_steps, save_interval=1, dtype=np.float64, a0=None,
                  snapshots=True):

@@ -11,11 +11,13 @@ from hpc.ensemble import generate_simulations, generate_single_simulation, simul
 
 
 @pytest.fixture()
-def fake(oracle_mod):
+def fake(oracle_mod, monkeypatch):
+    """The seam is in the TESTS: hpc._cuda.get_engine is patched to hand out the stand-in (the product has no
+    backend switch)."""
+    from hpc import _cuda
     eng = FakeEngine()
-    nbody._set_backend_for_tests(eng)
-    yield eng
-    nbody._set_backend_for_tests(None)
+    monkeypatch.setattr(_cuda, "get_engine", lambda device=None: eng)
+    return eng
 
 
 def test_constructor_draw_order_and_global_rng(fake, golden):
@@ -144,3 +146,87 @@ def test_batched_datagen_driver(fake, golden):
     out = simulate_ensemble(np.zeros((2, 3, 3)) + np.arange(3)[None, :, None], np.zeros((2, 3, 3)), np.ones(3) * 1e10,
                             n_steps=6, save_interval=3)
     assert out["positions"].shape == (2, 3, 3, 3) and np.array_equal(out["times"], [0.0, 0.003, 0.006])
+
+
+# ---- where the state lives between calls -----------------------------------------------------
+def _count(fake, what):
+    return sum(1 for c in fake.calls if c[0] == what)
+
+
+def test_step_loop_keeps_the_state_on_the_device(fake, oracle_mod):
+    """`for _ in range(k): sim.step()` (reference scripts/benchmark_bh_temp.py:24,32): one upload, no download until
+    the caller looks at the state."""
+    sim = nbody.NBodySimulator(n_particles=16, box_size=10.0, dt=0.001, seed=5)
+    x, v, a, m = (sim.positions.copy(), sim.velocities.copy(), sim.accelerations.copy(), sim.masses.copy())
+    fake.calls.clear()
+    for _ in range(25):
+        sim.step()
+    assert _count(fake, "resident") == 1 and _count(fake, "download") == 0 and _count(fake, "run") == 25
+    assert sim.step_count == 25
+    e = sim.get_energy()                                  # evaluated where the state is: still no download
+    assert _count(fake, "download") == 0
+    chk = oracle_mod.run(x, v, a, m, 0.001, 1e-9, 25, 25)
+    assert np.abs(sim.positions - chk["final_positions"]).max() < 1e-12      # first look: one download
+    assert _count(fake, "download") == 1
+    assert np.allclose(e, oracle_mod.total_energy(chk["final_positions"], chk["final_velocities"], m, 1e-9), rtol=1e-12)
+    sim.velocities, sim.accelerations                     # already current
+    assert _count(fake, "download") == 1
+    sim.run(5, verbose=False)                             # the caller has looked: the host copy may have been written
+    assert _count(fake, "resident") == 2
+
+
+def test_aliases_see_in_place_updates_and_writes_are_honoured(fake, oracle_mod):
+    sim = nbody.NBodySimulator(n_particles=12, box_size=10.0, dt=0.001, seed=9)
+    m, a0 = sim.masses.copy(), sim.accelerations.copy()
+    p = sim.positions                                     # an alias the caller keeps (a view counts too)
+    vview = sim.velocities[:4]
+    x0, v0 = p.copy(), sim.velocities.copy()
+    sim.step()
+    chk = oracle_mod.run(x0, v0, a0, m, 0.001, 1e-9, 1, 1)
+    assert np.array_equal(p, chk["final_positions"]) and np.array_equal(vview, chk["final_velocities"][:4])
+    assert sim.positions is p
+    # writing through the alias between steps changes the simulation, as it does in the reference
+    p[0, 0] += 0.5
+    x1 = p.copy()
+    v1 = sim.velocities.copy()
+    a1 = sim.accelerations.copy()
+    sim.step()
+    chk2 = oracle_mod.run(x1, v1, a1, m, 0.001, 1e-9, 1, 1)
+    assert np.array_equal(p, chk2["final_positions"])
+    del p, vview
+    # writing through the attribute without keeping a reference (the factories' pattern, nbody.py:294-300)
+    sim.positions[3, 1] = 7.25
+    x2, v2, a2 = sim.positions.copy(), sim.velocities.copy(), sim.accelerations.copy()
+    sim.step()
+    chk3 = oracle_mod.run(x2, v2, a2, m, 0.001, 1e-9, 1, 1)
+    assert np.array_equal(sim.positions, chk3["final_positions"])
+    # assigning masses (generate_data.py:46) re-uploads, keeps the dtype
+    n_up = _count(fake, "resident")
+    sim.masses = (m * 2).astype(np.float32)
+    sim.step()
+    assert _count(fake, "resident") == n_up + 1 and sim.masses.dtype == np.float32
+    # dt and softening are plain attributes read at every call
+    sim.dt = 0.002
+    t = sim.time
+    sim.step()
+    assert sim.time == t + 0.002
+
+
+def test_state_list_is_lazy_and_list_like(fake):
+    import pickle
+    sim = nbody.NBodySimulator(n_particles=10, box_size=10.0, dt=0.001, seed=3)
+    states = sim.run(30, save_interval=3, verbose=False)
+    assert isinstance(states, list) and len(states) == 11 and len(states._lazy) == 10     # nothing built yet
+    assert states[4]["step"] == 12 and not states._lazy                                    # built on first access
+    assert [s["step"] for s in states] == list(range(0, 31, 3))
+    assert all(s["positions"].flags.writeable and s["positions"].shape == (10, 3) for s in states)
+    states[2]["positions"][:] = -1.0                       # rows are disjoint: nothing else changes
+    assert (states[3]["positions"] != -1.0).all() and (states[1]["positions"] != -1.0).all()
+    assert (sim.positions != -1.0).all()
+    assert np.array_equal(states[-1]["positions"], sim.positions)
+    plain = pickle.loads(pickle.dumps(states))
+    assert type(plain) is list and len(plain) == 11 and np.array_equal(plain[5]["velocities"], states[5]["velocities"])
+    fresh = sim.run(4, verbose=False)
+    assert len(fresh + [1]) == 6 and len(fresh.copy()) == 5 and fresh[-1]["step"] == 34
+    stacked = np.stack([s["positions"] for s in sim.run(6, verbose=False)])      # generate_data.py:51
+    assert stacked.shape == (7, 10, 3)

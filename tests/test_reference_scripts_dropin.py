@@ -24,7 +24,8 @@ def test_generate_data_script_runs_unchanged(monkeypatch, tmp_path, oracle_mod, 
     import hpc.checkpoint           # sys.path.insert(0, <reference>/src) cannot shadow it
     from hpc import ics, nbody
     assert "nbody-gnn-hpc_b200" in hpc.__file__
-    nbody._set_backend_for_tests(FakeEngine())
+    fake = FakeEngine()
+    monkeypatch.setattr(hpc._cuda, "get_engine", lambda device=None: fake)    # the seam lives in the tests
     # the script prepends <reference>/src to sys.path and pins thread-count env vars: undo both afterwards
     monkeypatch.setattr(sys, "path", list(sys.path))
     for var in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
@@ -37,10 +38,7 @@ def test_generate_data_script_runs_unchanged(monkeypatch, tmp_path, oracle_mod, 
     monkeypatch.setattr(sys, "argv", ["generate_data.py", "--particles", "24", "--simulations", "5", "--steps", "12",
                                       "--workers", "1", "--output-dir", str(out), "--sequence-length", "5",
                                       "--batch-size", "2", "--seed", "42"])
-    try:
-        runpy.run_path(str(SCRIPT), run_name="__main__")
-    finally:
-        nbody._set_backend_for_tests(None)
+    runpy.run_path(str(SCRIPT), run_name="__main__")
     text = capsys.readouterr().out
     assert "DATA GENERATION COMPLETE" in text and "Generated 5 trajectories" in text
     mgr = hpc.checkpoint.CheckpointManager(str(out / "checkpoints"))
