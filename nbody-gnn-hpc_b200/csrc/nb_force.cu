@@ -31,7 +31,7 @@ constexpr int kStages = 4;
 constexpr int kTileBytes = 4096;
 
 // Stream the byte range [src, src + total_bytes) through the shared-memory ring, calling
-// consume(tile_ptr, tile_bytes) on every tile by all threads of the CTA.
+// consume(tile_ptr, tile_bytes, tile_index) on every tile by all threads of the CTA.
 template <class Consume>
 __device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int total_bytes, char* ring,
                                              uint64_t* bars, Consume&& consume) {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int t
         const int slot = t % kStages;
         mbar_wait(&bars[slot], (t / kStages) & 1);
         const int bytes = min(kTileBytes, total_bytes - t * kTileBytes);
-        consume(ring + slot * kTileBytes, bytes);
+        consume(ring + slot * kTileBytes, bytes, t);
         __syncthreads();  // every thread is done with this slot before it is refilled
         const int nt = t + kStages;
         if (threadIdx.x == 0 && nt < n_tiles) {
@@ -332,9 +332,14 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
     }
     const float2 e2 = make_float2(eps2, eps2);
 
-    auto consume = [&](const char* tile, int bytes) {
-        const float4* __restrict__ t = reinterpret_cast<const float4*>(tile);
-        const int n_pairs = bytes >> 5;
+    // The i == j term has r2 == eps2 and must contribute exactly 0 (the reference skips it, nbody.py:46).  dx = 0 is
+    // not enough: with eps = 1e-9, G*m*inv^3 overflows float32 for G*m > 3.4e11 (any star) and inf * 0 = NaN.  Testing
+    // every pair costs two ALU instructions per lane -- measured: 72 % -> 63 % of the FP32 peak at N = 65,536 -- so the
+    // test (r2 > eps2 ? inv : 0) is compiled only into a second copy of the loop, taken for the few j tiles that
+    // overlap this CTA's own bodies (a CTA-uniform branch per 4 KB tile).  eps == 0 needs nothing more: the same test
+    // removes r2 == 0.
+    const int own_lo = i0 + blockIdx.x * (kBlock * kP), own_hi = min(own_lo + kBlock * kP, i0 + n_i);
+    auto tile_loop = [&](const float4* __restrict__ t, int n_pairs, auto guard) {
 #pragma unroll 2
         for (int jp = 0; jp < n_pairs; ++jp) {
             const float4 A = t[2 * jp];      // x0 x1 y0 y1
@@ -352,12 +357,10 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
                 float2 inv;
                 inv.x = rsqrt_approx(r2.x);
                 inv.y = rsqrt_approx(r2.y);
-                // The i == j term (and exact overlaps) has r2 == eps2 and must contribute exactly 0 (the reference
-                // skips it, nbody.py:46).  dx = 0 is not enough: with eps = 1e-9, G*m*inv^3 overflows to inf for
-                // G*m > 3.4e11 (any star) and inf * 0 = NaN.  Two ALU-pipe instructions per lane, in issue slots the
-                // FMA-pipe-bound loop leaves free.  (kZeroEps is the same test with eps2 = 0.)
-                inv.x = (r2.x > eps2) ? inv.x : 0.f;
-                inv.y = (r2.y > eps2) ? inv.y : 0.f;
+                if (decltype(guard)::value) {
+                    inv.x = (r2.x > eps2) ? inv.x : 0.f;
+                    inv.y = (r2.y > eps2) ? inv.y : 0.f;
+                }
                 const float2 inv2 = __fmul2_rn(inv, inv);
                 float2 f = __fmul2_rn(gj, inv);
                 f = __fmul2_rn(f, inv2);
@@ -366,6 +369,13 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
                 az[k] = __ffma2_rn(f, dz, az[k]);
             }
         }
+    };
+    auto consume = [&](const char* tile, int bytes, int tile_index) {
+        const float4* __restrict__ t = reinterpret_cast<const float4*>(tile);
+        const int n_pairs = bytes >> 5;
+        const int jt_lo = j0 + tile_index * (kTileBytes / 16), jt_hi = jt_lo + 2 * n_pairs;
+        if (jt_lo < own_hi && own_lo < jt_hi) tile_loop(t, n_pairs, std::true_type{});
+        else tile_loop(t, n_pairs, std::false_type{});
     };
     stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 16, (j1 - j0) * 16, ring, bars, consume);
     pdl_release();
@@ -411,7 +421,7 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
         ax[k] = ay[k] = az[k] = 0.0;
     }
 
-    auto consume = [&](const char* tile, int bytes) {
+    auto consume = [&](const char* tile, int bytes, int) {
         const double2* __restrict__ t = reinterpret_cast<const double2*>(tile);
         const int n_j = bytes >> 5;
 #pragma unroll 4

@@ -178,15 +178,46 @@ class Engine:
             dev = dev.to(dtype)
         return dev
 
-    def _staging(self, nbytes: int):
-        """The engine's reusable pinned staging block (grown geometrically, never handed out)."""
+    def _staging(self, nbytes: int, which: str = "sync"):
+        """The engine's reusable pinned staging blocks (grown geometrically, never handed out): one for the
+        synchronous to_host, one for the single to_host_async that may be in flight at a time."""
         torch = _torch()
-        buf = getattr(self, "_stage_buf", None)
+        bufs = self.__dict__.setdefault("_stage_bufs", {})
+        buf = bufs.get(which)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 1 << 20, 2 * (buf.numel() if buf is not None else 0)),
                               dtype=torch.uint8, pin_memory=True)
-            self._stage_buf = buf
+            bufs[which] = buf
         return buf
+
+    def to_host_async(self, t):
+        """to_host in two halves: the device -> pinned host copy is enqueued now; the returned callable waits for
+        it and returns the host array (same policy as to_host)."""
+        torch = _torch()
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        t = t.contiguous()
+        nbytes = t.numel() * 8
+        stream = torch.cuda.current_stream(self.device)
+        if nbytes <= PAGEABLE_RESULT_MAX_BYTES:
+            stage = self._staging(nbytes, "async")[:nbytes].view(torch.float64).view(t.shape)
+            stage.copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+
+            def finish():
+                done.synchronize()
+                return stage.numpy().copy()
+            return finish
+        host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(stream)
+
+        def finish_pinned():
+            done.synchronize()
+            return host.numpy()
+        return finish_pinned
 
     def to_host(self, t, pinned: bool = True) -> np.ndarray:
         """Device tensor -> fresh host float64 ndarray.
@@ -546,6 +577,8 @@ class ResidentSystem:
         pos = np.ascontiguousarray(positions, dtype=np.float64)
         self.n = n = pos.shape[0]
         self.small = n <= SMALL_SYSTEM_MAX_BODIES
+        self._step_call = None
+        self._index = eng.device.index or 0
         xva = np.stack([pos, np.asarray(velocities, dtype=np.float64), np.asarray(accelerations, dtype=np.float64)])
         with torch.cuda.device(eng.device):
             self.m_d, self.m_f32 = eng._masses_dev(masses)
@@ -562,10 +595,45 @@ class ResidentSystem:
                 self.acc = xva_d[2].to(td) if td != torch.float64 else xva_d[2].clone()
                 self.ws = eng.workspace(n, n, self.dtype)
 
+    def step(self) -> None:
+        """One kick-drift-kick step, nothing returned: the per-call path of `for ...: sim.step()`.  The C call and
+        its arguments are prepared once; per step only dt, softening and the current stream are refreshed."""
+        torch = _torch()
+        eng = self.eng
+        if not self.small:
+            self.advance(1)
+            return
+        call = self._step_call
+        if call is None:
+            fn = getattr(eng.lib, "nb_ensemble_" + eng._suffix(self.dtype))
+            P = eng._p
+            call = self._step_call = [fn, [P(self.xva[0]), P(self.xva[1]), P(self.xva[2]), P(self.m_d), self.m_f32, 0, 1,
+                                           self.n, 0.0, 0.0, 1, 1, 0, 0, None, None, None, 0, 0, P(self.ws[0]),
+                                           self.ws[1], None]]
+        fn, args = call
+        args[8], args[9] = self.dt, self.softening
+        if torch.cuda.current_device() == self._index:
+            args[21] = torch.cuda.current_stream().cuda_stream
+            rc = fn(*args)
+        else:
+            with torch.cuda.device(eng.device):
+                args[21] = torch.cuda.current_stream().cuda_stream
+                rc = fn(*args)
+        if rc:
+            eng._check(rc)
+        eng.launches += 1
+
     def advance(self, n_steps: int, save_interval: int = 1, snapshots: bool = False):
         """n_steps kick-drift-kick steps on the device.  snapshots=True: returns {'positions','velocities',
         'accelerations'}: host stacks (1 + n_steps // save_interval, N, 3) float64, row 0 = the state on entry
         (one device -> host copy for all three)."""
+        pending = self.advance_async(n_steps, save_interval, snapshots)
+        return pending() if pending is not None else None
+
+    def advance_async(self, n_steps: int, save_interval: int = 1, snapshots: bool = False):
+        """advance() in two halves: everything is enqueued here (kernels and, with snapshots, the device -> pinned
+        host copy); the returned callable waits for it and hands out the host stacks.  Host-side bookkeeping done
+        between the two overlaps the GPU."""
         torch = _torch()
         eng, n = self.eng, self.n
         n_snap = 1 + n_steps // save_interval
@@ -586,8 +654,12 @@ class ResidentSystem:
                     self.cur, self.nxt = self.nxt, self.cur
             if not snapshots:
                 return None
-            host = eng.to_host(snaps)
-        return {"positions": host[0], "velocities": host[1], "accelerations": host[2]}
+            finish = eng.to_host_async(snaps)
+
+        def wait():
+            host = finish()
+            return {"positions": host[0], "velocities": host[1], "accelerations": host[2]}
+        return wait
 
     def download(self):
         """(positions, velocities, accelerations): fresh host float64 (N,3) arrays of the current state."""

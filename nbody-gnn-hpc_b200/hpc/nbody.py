@@ -91,6 +91,19 @@ def _refs(holder: dict, name: str) -> int:
 _UNSHARED_REFS = _refs({"x": np.zeros(1)}, "x")
 
 
+class _Pending:
+    """Snapshot stacks of one device segment: a callable that waits for them, then the stacks themselves."""
+    __slots__ = ("_wait", "_value")
+
+    def __init__(self, wait):
+        self._wait, self._value = wait, None
+
+    def get(self) -> dict:
+        if self._wait is not None:
+            self._value, self._wait = self._wait(), None
+        return self._value
+
+
 class StateList(list):
     """The list ``NBodySimulator.run`` returns (reference nbody.py:232-248): one state dictionary per saved step,
     built when it is first accessed.  The snapshots arrive from the device as three stacked arrays; a state's
@@ -110,7 +123,8 @@ class StateList(list):
 
     def _materialise(self) -> None:
         if self._lazy:
-            for idx, stacks, r, t, k in self._lazy:
+            for idx, pending, r, t, k in self._lazy:
+                stacks = pending.get()
                 super().__setitem__(idx, {
                     'positions': stacks['positions'][r],
                     'velocities': stacks['velocities'][r],
@@ -319,21 +333,29 @@ class NBodySimulator:
         h = self._host
         return self._engine().accelerations(h["positions"], h["masses"], float(self.softening), self.dtype)
 
-    def _advance(self, n_steps: int, save_interval: int, snapshots: bool) -> Optional[dict]:
-        """n_steps on the device; the live state stays there (host arrays refreshed only while aliased)."""
+    def _advance(self, n_steps: int, save_interval: int, snapshots: bool):
+        """n_steps on the device; the live state stays there (host arrays refreshed only while aliased).  With
+        snapshots, returns a callable that waits for the device and hands out the host stacks."""
         rs = self._device_state()
-        out = rs.advance(int(n_steps), int(save_interval), snapshots=snapshots)
+        pending = rs.advance_async(int(n_steps), int(save_interval), snapshots=snapshots)
         self._host_stale = True
+        t, dt = self.time, self.dt
         for _ in range(n_steps):
-            self.time += self.dt          # a running float sum, reference nbody.py:217
+            t += dt                       # a running float sum, reference nbody.py:217
+        self.time = t
         self.step_count += n_steps
         if self._aliased():
             self._sync_host()             # in place, as the reference's  +=  updates are
-        return out
+        return pending
 
     def step(self) -> None:
         """Advance the simulation by one kick-drift-kick step (reference nbody.py:202-218)."""
-        self._advance(1, 1, snapshots=False)
+        self._device_state().step()
+        self._host_stale = True
+        self.time += self.dt              # reference nbody.py:217
+        self.step_count += 1
+        if self._aliased():
+            self._sync_host()             # in place, as the reference's  +=  updates are
 
     def run(self, n_steps: int, save_interval: int = 1, verbose: bool = True) -> list:
         """Run n_steps, returning the list of saved states (reference nbody.py:220-248).
@@ -360,17 +382,19 @@ class NBodySimulator:
             phase = done % save_interval
             if phase:  # a report point fell between two save points: walk to the next save point first
                 lead = min(save_interval - phase, seg)
-                out = self._advance(lead, lead, snapshots=True)
+                out = _Pending(self._advance(lead, lead, snapshots=True))
                 done += lead
                 seg -= lead
                 if done % save_interval == 0:
                     states._append_rows(out, [1], [times[done]], [s0 + done])
+                out.get()                 # the pinned staging block is reused by the next segment
             if seg > 0:
-                out = self._advance(seg, save_interval, snapshots=True)
+                out = _Pending(self._advance(seg, save_interval, snapshots=True))
                 rows = range(1, seg // save_interval + 1)
                 ks = [done + r * save_interval for r in rows]
-                states._append_rows(out, rows, [times[k] for k in ks], [s0 + k for k in ks])
+                states._append_rows(out, rows, [times[k] for k in ks], [s0 + k for k in ks])   # overlaps the GPU
                 done += seg
+                out.get()                 # the segment is complete (and its snapshots on the host) before we go on
             if verbose and done % report == 0:
                 energy = self.get_energy()
                 print(f"Step {done}/{n_steps}, Time: {self.time:.4f}, Energy: {energy[2]:.6e}")

@@ -29,6 +29,13 @@ class FakeResident:
             return {k: out[k] for k in ("positions", "velocities", "accelerations")}
         return None
 
+    def advance_async(self, n_steps, save_interval=1, snapshots=False):
+        out = self.advance(n_steps, save_interval, snapshots)
+        return (lambda: out) if snapshots else None
+
+    def step(self):
+        self.advance(1)
+
     def download(self):
         self.eng.calls.append(("download",))
         return self.x.copy(), self.v.copy(), self.a.copy()
