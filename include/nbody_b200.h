@@ -60,6 +60,10 @@ int nb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
  * 1 = packed FFMA2 (f32x2), 2 = DFMA.  scratch: one float on the device.  Synchronises. */
 int nb_probe_fma_peak(int mode, double* tflops, float* scratch, nb_stream_t s);
 
+/* Test aid: n_ctas thread blocks that each hold smem_bytes of shared memory and spin for `milliseconds` (<= 5000)
+ * on stream s -- "another tenant's kernel" for the tests of the launches that need all their blocks resident. */
+int nb_probe_occupy(int n_ctas, size_t smem_bytes, double milliseconds, nb_stream_t s);
+
 /* ---- planning: pure host arithmetic, callable without a GPU ------------------------------ */
 /* Padded system length (multiple of NB_CHUNK_BODIES, at least one chunk). */
 int nb_padded_bodies(int n);

@@ -55,6 +55,10 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "nb_common.cuh"
 
 namespace nb {
@@ -641,6 +645,84 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const 
 
 constexpr int kEnsembleMaxBodies = 1024;
 
+// ------------------------------------------------------------------------------------------------------------------
+// launch plans
+// ------------------------------------------------------------------------------------------------------------------
+struct LaunchPlan {
+    void (*kern)(const EnsembleArgs);
+    int cluster;  // CTAs per system (8, 4, 2), or 0: the persistent one-CTA-per-SM kernel
+    int threads;
+    size_t smem;
+    int lanes;    // persistent kernel: systems advanced side by side by one CTA
+    int grid;     // persistent kernel: CTAs
+};
+using PlanKey = std::tuple<int, int, int, int, int>;  // device, sizeof(T), B, N, flags
+static std::mutex g_plan_mutex;
+static std::map<PlanKey, LaunchPlan> g_plans;
+
+template <typename T>
+static int make_plan(int dev, int B, int N, int parts, int f_threads, bool zero, bool no_cluster, LaunchPlan* out) {
+    int sms = 0, smem_max = 0;
+    NB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NB_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // Few systems: one system per cluster of 8, 4 or 2 CTAs (distributed shared memory) -- the largest cluster that
+    // still gives every system its own -- if the slab shape fits a CTA.
+    for (int C = kClusterCtas; C >= 2 && !no_cluster; C /= 2) {
+        if ((long)B * C > sms) continue;
+        const int S = ceil_div(N, C);
+        const int c_threads = round_up(S * parts > 3 * S ? S * parts : 3 * S, 32);
+        const size_t c_smem = cluster_smem_bytes<T>(N, parts, C);
+        if (N < 2 * C || c_threads > 1024 || c_smem + 1024 > (size_t)smem_max) continue;
+        void (*ck)(const EnsembleArgs);
+        if (c_threads <= 256)
+            ck = zero ? cluster_ensemble_kernel<T, true, 256> : cluster_ensemble_kernel<T, false, 256>;
+        else
+            ck = zero ? cluster_ensemble_kernel<T, true, 1024> : cluster_ensemble_kernel<T, false, 1024>;
+        // the permission is set to the device maximum once: plans of other N share the kernel
+        NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B * C);
+        cfg.blockDim = dim3(c_threads);
+        cfg.dynamicSmemBytes = c_smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        // every system's cluster must be resident at once (clusters are placed inside a GPC, so fewer fit than
+        // SMs / C: 37 clusters of 4 ran in two waves, 2.1 ms against 1.8 ms on clusters of 2)
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= B) {
+            *out = LaunchPlan{ck, C, c_threads, c_smem, 1, 0};
+            return NB_OK;
+        }
+        (void)cudaGetLastError();  // not all clusters of this size can be placed at once: try smaller, then one CTA
+    }
+    // Two lanes + the integrator warps when there are systems for 2 x SMs workers and both lanes fit in shared
+    // memory; else one lane, every thread in both phases.
+    const size_t lane_bytes = lane_smem_bytes<T>(N, parts);
+    const int lanes = (B >= 2 * sms && 2 * lane_bytes + 1024 <= (size_t)smem_max) ? 2 : 1;
+    const int threads = f_threads + (lanes == 2 ? kIntegratorThreads : 0);
+    const size_t smem = (size_t)lanes * lane_bytes;
+    void (*kern)(const EnsembleArgs);
+    const bool split = lanes == 2;
+    if (N == 200 && !zero)  // the reference's data-generation shape (generate_data.py:109), compiled with constant bounds
+        kern = split ? ensemble_kernel<T, false, 200, true> : ensemble_kernel<T, false, 200, false>;
+    else if (split)
+        kern = zero ? ensemble_kernel<T, true, 0, true> : ensemble_kernel<T, false, 0, true>;
+    else
+        kern = zero ? ensemble_kernel<T, true, 0, false> : ensemble_kernel<T, false, 0, false>;
+    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024));
+    int per_sm = 0;
+    NB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    NB_REQUIRE(per_sm >= 1, "ensemble kernel does not fit on an SM (N=%d threads=%d smem=%zu)", N, threads, smem);
+    // persistent grid, one CTA per SM; with fewer systems than SMs, one system per CTA
+    *out = LaunchPlan{kern, 0, threads, smem, lanes, B < sms ? B : sms};
+    return NB_OK;
+}
+
 template <typename T>
 static int ensemble_impl(double* x, double* v, double* a, const void* masses, int masses_are_f32, int mass_stride, int B,
                          int N, double dt, double softening, int n_steps, int save_interval, int compute_a0,
@@ -672,75 +754,64 @@ static int ensemble_impl(double* x, double* v, double* a, const void* masses, in
     static_assert(200 % shape_parts(200) == 0, "the static N=200 shape needs equal j-parts");
     g.f_threads = round_up(g.rows * parts, 32);
     const bool zero = !((T)g.eps2 > T(0));
-    int dev = 0, sms = 0, smem_max = 0;
+    int dev = 0;
     NB_CUDA_OK(cudaGetDevice(&dev));
-    NB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    NB_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // Few systems: one system per cluster of 8, 4 or 2 CTAs (distributed shared memory) -- the largest cluster that
-    // still gives every system its own -- if the slab shape fits a CTA.
-    for (int C = kClusterCtas; C >= 2 && getenv("NB_ENSEMBLE_NO_CLUSTER") == nullptr; C /= 2) {
-        if ((long)B * C > sms) continue;
-        const int S = ceil_div(N, C);
-        const int c_threads = round_up(S * parts > 3 * S ? S * parts : 3 * S, 32);
-        const size_t c_smem = cluster_smem_bytes<T>(N, parts, C);
-        if (N < 2 * C || c_threads > 1024 || c_smem + 1024 > (size_t)smem_max) continue;
-        void (*ck)(const EnsembleArgs);
-        if (c_threads <= 256)
-            ck = zero ? cluster_ensemble_kernel<T, true, 256> : cluster_ensemble_kernel<T, false, 256>;
-        else
-            ck = zero ? cluster_ensemble_kernel<T, true, 1024> : cluster_ensemble_kernel<T, false, 1024>;
-        NB_CUDA_OK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c_smem));
+    // Which kernel, cluster size, block size and shared memory this (device, precision, B, N) gets is decided once
+    // (occupancy queries and function attributes cost more host time than a one-step launch) and remembered.
+    const bool no_cluster = getenv("NB_ENSEMBLE_NO_CLUSTER") != nullptr;
+    const PlanKey key{dev, (int)sizeof(T), B, N, (zero ? 1 : 0) | (no_cluster ? 2 : 0)};
+    LaunchPlan plan;
+    bool have = false;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        auto it = g_plans.find(key);
+        if (it != g_plans.end()) { plan = it->second; have = true; }
+    }
+    if (!have) {
+        if (int rc = make_plan<T>(dev, B, N, parts, g.f_threads, zero, no_cluster, &plan)) return rc;
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plans[key] = plan;
+    }
+    g.lanes = plan.lanes;
+    g.progress = nullptr;
+    if (plan.cluster > 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(B * C);
-        cfg.blockDim = dim3(c_threads);
-        cfg.dynamicSmemBytes = c_smem;
+        cfg.gridDim = dim3(B * plan.cluster);
+        cfg.blockDim = dim3(plan.threads);
+        cfg.dynamicSmemBytes = plan.smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = C;
+        attr[0].val.clusterDim.x = plan.cluster;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        int n_clusters = 0;
-        // every system's cluster must be resident at once (clusters are placed inside a GPC, so fewer fit than
-        // SMs / C: 37 clusters of 4 ran in two waves, 2.1 ms against 1.8 ms on clusters of 2)
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, ck, &cfg) == cudaSuccess && n_clusters >= B) {
-            g.lanes = 1; g.progress = nullptr;
-            NB_CUDA_OK(cudaLaunchKernelEx(&cfg, ck, g));
-            return check_launch("cluster ensemble kernel");
-        }
-        (void)cudaGetLastError();  // not all clusters of this size can be placed at once: try smaller, then one CTA
+        NB_CUDA_OK(cudaLaunchKernelEx(&cfg, plan.kern, g));
+        return check_launch("cluster ensemble kernel");
     }
-    // Two lanes + the integrator warp when there are systems for 2 x SMs workers and both lanes fit in shared
-    // memory; else one lane, every thread in both phases.
-    const size_t lane_bytes = lane_smem_bytes<T>(N, parts);
-    g.lanes = (B >= 2 * sms && 2 * lane_bytes + 1024 <= (size_t)smem_max) ? 2 : 1;
-    const int threads = g.f_threads + (g.lanes == 2 ? kIntegratorThreads : 0);
-    const size_t smem = (size_t)g.lanes * lane_bytes;
-    void (*kern)(const EnsembleArgs);
-    const bool split = g.lanes == 2;
-    if (N == 200 && !zero)  // the reference's data-generation shape (generate_data.py:109), compiled with constant bounds
-        kern = split ? ensemble_kernel<T, false, 200, true> : ensemble_kernel<T, false, 200, false>;
-    else if (split)
-        kern = zero ? ensemble_kernel<T, true, 0, true> : ensemble_kernel<T, false, 0, true>;
-    else
-        kern = zero ? ensemble_kernel<T, true, 0, false> : ensemble_kernel<T, false, 0, false>;
-    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    NB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    NB_REQUIRE(per_sm >= 1, "ensemble kernel does not fit on an SM (N=%d threads=%d smem=%zu)", N, threads, smem);
-    // persistent grid, one CTA per SM; with fewer systems than SMs, one system per CTA
-    const int grid = B < sms ? B : sms;
     // A system is shared by two workers whenever the B x n_steps line does not divide evenly: per-system flags
-    g.progress = nullptr;
-    if (B % (grid * g.lanes) != 0) {
+    if (B % (plan.grid * g.lanes) != 0) {
         NB_REQUIRE(ws && ws_bytes >= nb_ensemble_workspace_bytes(B), "ensemble workspace too small: %zu < %zu",
                    ws_bytes, nb_ensemble_workspace_bytes(B));
         g.progress = static_cast<int*>(ws);
         NB_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(int) * (size_t)B, st));
     }
-    kern<<<grid, threads, smem, st>>>(g);
+    // Workers hand systems to each other through the flags and spin on them: every CTA of the grid must be resident
+    // at once.  A COOPERATIVE launch guarantees that (the grid waits until it can be placed as a whole, and a grid
+    // that can never be is refused with an error) -- a plain launch next to another stream's kernels or under MPS
+    // would leave tail workers spinning for CTAs that are not running.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(plan.threads);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = g.progress != nullptr ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NB_CUDA_OK(cudaLaunchKernelEx(&cfg, plan.kern, g));
     return check_launch("ensemble kernel");
 }
 

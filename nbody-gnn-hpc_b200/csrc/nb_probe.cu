@@ -78,3 +78,27 @@ extern "C" int nb_probe_fma_peak(int mode, double* tflops, float* scratch, nb_st
     *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
     return nb::check_launch("fma probe");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// nb_probe_occupy: n_ctas thread blocks that each hold smem_bytes of shared memory and spin for `milliseconds`.
+// A stand-in for "somebody else's kernel is on the GPU" in the tests of the launches that need co-residency.
+// ---------------------------------------------------------------------------------------------------------------
+namespace nb {
+__global__ void occupy_kernel(unsigned long long ns) {
+    extern __shared__ char hold[];
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (threadIdx.x == 0) hold[0] = 1;
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+}  // namespace nb
+
+extern "C" int nb_probe_occupy(int n_ctas, size_t smem_bytes, double milliseconds, nb_stream_t s) {
+    NB_REQUIRE(n_ctas > 0 && milliseconds >= 0.0 && milliseconds <= 5000.0, "nb_probe_occupy: bad argument");
+    NB_CUDA_OK(cudaFuncSetAttribute(nb::occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    nb::occupy_kernel<<<n_ctas, 32, smem_bytes, (cudaStream_t)s>>>((unsigned long long)(milliseconds * 1e6));
+    return nb::check_launch("occupy kernel");
+}

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import sys
 import threading
 from pathlib import Path
 
@@ -32,6 +33,16 @@ SMALL_SYSTEM_MAX_BODIES = 640
 # Host results up to this size are ordinary pageable arrays (copied out of a reusable pinned staging block); larger
 # ones are views of their own pinned block (see Engine.to_host).
 PAGEABLE_RESULT_MAX_BYTES = 64 << 20
+HOST_POOL_MAX_BYTES = 256 << 20
+
+
+def _pool_refs(entry) -> int:
+    """References to a pooled host array as _host_block sees them."""
+    return sys.getrefcount(entry[1])
+
+
+# what _pool_refs reports when nobody outside the pool refers to the array or a view of it (measured, not assumed)
+_POOL_IDLE_REFS = _pool_refs((None, np.zeros(1)))
 
 
 class EngineUnavailable(RuntimeError):
@@ -46,6 +57,7 @@ _SIGNATURES = {
     "nb_last_error": (ctypes.c_char_p, []),
     "nb_device_info": (_ci, [_ci, _ip, _ip, _ip, _ip]),
     "nb_probe_fma_peak": (_ci, [_ci, ctypes.POINTER(ctypes.c_double), _vp, _vp]),
+    "nb_probe_occupy": (_ci, [_ci, _sz, _cd, _vp]),
     "nb_padded_bodies": (_ci, [_ci]),
     "nb_segment_plan": (_ci, [_ci, _ip, _ip]),
     "nb_workspace_bytes": (_sz, [_ci, _ci, _ci]),
@@ -119,6 +131,11 @@ def _torch():
     return torch
 
 
+def _current_device(torch) -> int:
+    get = getattr(torch._C, "_cuda_getDevice", None)
+    return int(get()) if get is not None else int(torch.cuda.current_device())
+
+
 class Engine:
     """One CUDA device's view of the library.  Mirrors the reference operations one to one."""
 
@@ -144,8 +161,17 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f"libnbody_b200: {self.lib.nb_last_error().decode()} (code {rc})")
 
+    def _raw_stream(self) -> int:
+        """cudaStream_t of torch's current stream on this engine's device, as an int (the fast getter when this
+        torch build has it: the public wrappers cost several microseconds per call)."""
+        torch = _torch()
+        get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if get is not None:
+            return int(get(self.device.index or 0))
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
     def _stream(self):
-        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(self._raw_stream())
 
     @staticmethod
     def _p(t):
@@ -190,6 +216,32 @@ class Engine:
             bufs[which] = buf
         return buf
 
+    def _host_block(self, nbytes: int) -> np.ndarray:
+        """A host block of nbytes for a result that is handed out: page-locked, from a small pool.
+
+        A fresh pageable array costs a page fault per 4 KB on first touch (0.4 ms for the 1.15 MB of a 400-step
+        N = 200 run -- half the kernel time), a fresh pinned block a cudaHostAlloc.  So blocks are pooled and a block
+        is reused once NOBODY outside the pool refers to it or to a view of it any more (reference count).  The pool
+        is bounded (HOST_POOL_MAX_BYTES); when it is full of blocks still in use, the result is an ordinary array."""
+        torch = _torch()
+        pool = self.__dict__.setdefault("_host_pool", [])
+        best = None
+        for ent in pool:
+            size = ent[1].nbytes
+            if nbytes <= size <= max(4 * nbytes, 1 << 16) and _pool_refs(ent) <= _POOL_IDLE_REFS:
+                if best is None or size < best[1].nbytes:
+                    best = ent
+        if best is None:
+            # drop idle blocks that are too small, then add one if the budget allows
+            pool[:] = [e for e in pool if _pool_refs(e) > _POOL_IDLE_REFS or e[1].nbytes >= nbytes]
+            used = sum(e[1].nbytes for e in pool)
+            if used + nbytes > HOST_POOL_MAX_BYTES:
+                return np.empty(nbytes, dtype=np.uint8)
+            tens = torch.empty(max(nbytes, 1 << 12), dtype=torch.uint8, pin_memory=True)
+            best = (tens, tens.numpy())
+            pool.append(best)
+        return best[1][:nbytes]
+
     def to_host_async(self, t):
         """to_host in two halves: the device -> pinned host copy is enqueued now; the returned callable waits for
         it and returns the host array (same policy as to_host)."""
@@ -200,6 +252,18 @@ class Engine:
         nbytes = t.numel() * 8
         stream = torch.cuda.current_stream(self.device)
         if nbytes <= PAGEABLE_RESULT_MAX_BYTES:
+            block = self._host_block(nbytes)                      # pooled: no page faults, no second copy
+            if block.base is not None:                            # page-locked: copy straight into it
+                out = block.view(np.float64).reshape(tuple(t.shape))
+                torch.from_numpy(out).copy_(t, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(stream)
+                del block
+
+                def finish_pooled():
+                    done.synchronize()
+                    return out
+                return finish_pooled
             stage = self._staging(nbytes, "async")[:nbytes].view(torch.float64).view(t.shape)
             stage.copy_(t, non_blocking=True)
             done = torch.cuda.Event()
@@ -207,7 +271,9 @@ class Engine:
 
             def finish():
                 done.synchronize()
-                return stage.numpy().copy()
+                out = block.view(np.float64).reshape(tuple(t.shape))
+                out[...] = stage.numpy()
+                return out
             return finish
         host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
         host.copy_(t, non_blocking=True)
@@ -222,11 +288,12 @@ class Engine:
     def to_host(self, t, pinned: bool = True) -> np.ndarray:
         """Device tensor -> fresh host float64 ndarray.
 
-        Up to PAGEABLE_RESULT_MAX_BYTES the copy goes through the engine's reusable pinned staging block into an
-        ordinary (pageable) array, so retained results do not keep memory page-locked.  Larger results (the 1.7 GB
-        snapshot stacks of an ensemble) are handed out as views of their own pinned block: a second pass over them
-        on the host would cost several times the whole GPU run; such an array keeps its block page-locked for as
-        long as it is alive (np.array(x) makes a pageable copy)."""
+        Up to PAGEABLE_RESULT_MAX_BYTES the result lives in a block of the engine's bounded pool of page-locked
+        host blocks (_host_block: reused when the caller has dropped the previous result, at most
+        HOST_POOL_MAX_BYTES in total, ordinary arrays beyond that).  Larger results (the 1.7 GB snapshot stacks
+        of an ensemble) are views of their own pinned block: a second pass over them on the host would cost several
+        times the whole GPU run; such an array keeps its block page-locked for as long as it is alive (np.array(x)
+        makes a pageable copy)."""
         torch = _torch()
         if t.dtype != torch.float64:
             t = t.to(torch.float64)
@@ -235,10 +302,7 @@ class Engine:
         if not pinned or nbytes < (1 << 12):
             return t.cpu().numpy()
         if nbytes <= PAGEABLE_RESULT_MAX_BYTES:
-            stage = self._staging(nbytes)[:nbytes].view(torch.float64).view(t.shape)
-            stage.copy_(t, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            return stage.numpy().copy()
+            return self.to_host_async(t)()
         host = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)
         host.copy_(t, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -612,12 +676,12 @@ class ResidentSystem:
                                            self.ws[1], None]]
         fn, args = call
         args[8], args[9] = self.dt, self.softening
-        if torch.cuda.current_device() == self._index:
-            args[21] = torch.cuda.current_stream().cuda_stream
+        if _current_device(torch) == self._index:
+            args[21] = eng._raw_stream()
             rc = fn(*args)
         else:
             with torch.cuda.device(eng.device):
-                args[21] = torch.cuda.current_stream().cuda_stream
+                args[21] = eng._raw_stream()
                 rc = fn(*args)
         if rc:
             eng._check(rc)

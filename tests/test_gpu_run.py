@@ -457,3 +457,30 @@ def test_cluster_sizes_bitwise_equal_one_cta_kernel(engine, monkeypatch, B):
     one = simulate_ensemble(x0, v0, m32, **kw)
     for key in ("positions", "velocities", "accelerations", "final_positions", "final_velocities", "final_accelerations"):
         assert np.array_equal(clu[key], one[key]), (B, key)
+
+
+def test_interval_schedule_with_another_tenant_on_the_gpu(engine):
+    """The persistent ensemble kernel's workers hand systems to each other through flags and spin on them: every CTA
+    must be resident at once.  With half the SMs held by another stream's kernel for 300 ms (nb_probe_occupy: one
+    CTA per SM holding 200 KB of shared memory) the launch -- cooperative whenever systems are shared -- still
+    completes, with the bits of the undisturbed run, instead of tail workers spinning for CTAs that are not running."""
+    import ctypes
+    import torch
+    from hpc import ics
+    from hpc.ensemble import simulate_ensemble
+    B = 2 * engine.sm_count + 9                     # more systems than workers: hand-over flags in use
+    x0, v0, m32 = ics.datagen_ensemble_ic(B, 200, seed=77)
+    kw = dict(dt=1e-3, softening=1e-9, n_steps=30, save_interval=5)
+    quiet = simulate_ensemble(x0, v0, m32, **kw)
+    other = torch.cuda.Stream()
+    rc = engine.lib.nb_probe_occupy(engine.sm_count // 2, 200 * 1024, 300.0, ctypes.c_void_p(other.cuda_stream))
+    assert rc == 0, engine.lib.nb_last_error()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    busy = simulate_ensemble(x0, v0, m32, **kw)
+    t1.record()
+    torch.cuda.synchronize()
+    for key in ("positions", "velocities", "accelerations", "final_positions"):
+        assert np.array_equal(busy[key], quiet[key]), key
+    assert t0.elapsed_time(t1) < 3000.0
