@@ -482,6 +482,7 @@ def bench_ensemble(args, world, rank, local):
         if rank == 0 and world == 1:
             extra.update(single_system_extras(eng))
             extra["window_gather_300x401x200_L10"] = window_extras(eng, outs[0][0], outs[0][1])
+            extra["snapshot_energies_300x401x200"] = snapshot_energy_extras(eng, outs[0][0], outs[0][1], m32)
             extra["e2e_device_resident"] = device_resident_extras(eng, x0, v0, m32, dtype, inter_step)
             extra["simulator_api_N200_400_steps"] = simulator_api_extras(local, numba_api_ms)
         del outs
@@ -537,6 +538,31 @@ def window_extras(eng, pos_d, vel_d) -> dict:
     return {"ms": round(ms, 4), "samples": int(ins.shape[0]), "algorithmic_bytes": bytes_alg,
             "achieved_GBps": round(gbs, 1), "hbm_peak_GBps": peaks["hbm_gbs"], "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
             "device_fill_of_the_outputs_GBps": round(fill_gbs, 1), "l2": "6.2 GB written per launch (>> 126 MB L2)"}
+
+
+def snapshot_energy_extras(eng, pos_d, vel_d, m32) -> dict:
+    """K4b: energy and momentum of all 300 x 401 snapshots the timed kernel just wrote, one launch --
+    what 300 calls of the reference's compute_energy_error (src/utils/metrics.py:62-109) evaluate on the host."""
+    import torch
+    m_d, f32 = eng._masses_dev(m32)
+    B, S, N = int(pos_d.shape[0]), int(pos_d.shape[1]), int(pos_d.shape[2])
+    eng.snapshot_energies(pos_d, vel_d, m_d, f32, 0, 1e-9)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        eng.snapshot_energies(pos_d, vel_d, m_d, f32, 0, 1e-9)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pairs = B * S * N * (N - 1) / 2.0
+    peaks = measured_peaks()
+    ops = 14.0                                   # FP64-pipe operations per pair term (3 sub, 3 fma, 6 rsqrt chain, mul, add)
+    peak_ops = eng.sm_count * 64 * peaks["sm_max_mhz"] * 1e6
+    return {"ms": round(ms, 4), "snapshots": B * S, "pair_terms_per_s": round(pairs / ms * 1e3, 1),
+            "fp64_ops_per_pair_term": ops, "frac_of_fp64_pipe_issue_peak": round(pairs * ops / (ms * 1e-3) / peak_ops, 4),
+            "hbm_bytes_read": int(2 * pos_d.numel() * 8), "hbm_GBps": round(2 * pos_d.numel() * 8 / ms / 1e6, 1)}
 
 
 def device_resident_extras(eng, x0, v0, m32, dtype, inter_step) -> dict:

@@ -214,6 +214,20 @@ int nb_energy_f64(const double* pos, const double* vel, const void* masses, int 
                   int n, int i0, int n_i, double softening, double* out_ku,
                   void* workspace, size_t workspace_bytes, nb_stream_t s);
 
+/* K4b: energy and momentum of EVERY snapshot of a stack of trajectories.  Replaces compute_energy_error, reference
+ * src/utils/metrics.py:62-109 (a Python loop over the stored steps with an N x N x 3 temporary per step), and
+ * compute_momentum_error, :112-137, for B trajectories x S snapshots in one launch:
+ *   pos, vel   (B, S, N, 3) float64 device stacks (what nb_ensemble_* writes); pos may be NULL: K and p only, U = 0
+ *   masses     (N) shared (mass_stride 0) or (B, N) (mass_stride N); f64 or f32 (f32: m_i*m_j is rounded to float32,
+ *              as np.outer of the reference's float32 mass array is, metrics.py:82)
+ *   G          the constant of metrics.py:65 (NB_G by default there)
+ *   out        (B, S, 5) float64 device: K, U, px, py, pz of every snapshot
+ * N <= nb_snapshot_energy_max_bodies() (a snapshot lives in shared memory); larger systems: nb_energy_f64 per state. */
+int nb_snapshot_energy_max_bodies(void);
+int nb_snapshot_energy_f64(const double* pos, const double* vel, const void* masses, int masses_are_f32,
+                           int mass_stride, int B, int S, int N, double G, double softening, double* out,
+                           nb_stream_t s);
+
 /* ---- K5: sliding-window training samples --------------------------------------------------------
  * Replaces the sample loop of create_training_dataset, reference src/hpc/checkpoint.py:362-384
  * (and the sample count of :333): for every trajectory b of an ensemble whose float64 snapshot stacks

@@ -132,3 +132,107 @@ int nb_energy_f64(const double* pos, const double* vel, const void* masses, int 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// K4b -- energy and momentum of EVERY snapshot of a stack of trajectories.
+//
+// Replaces compute_energy_error (reference src/utils/metrics.py:62-109: a Python loop over the stored steps with an
+// N x N x 3 temporary per step) and compute_momentum_error (:112-137) for B trajectories x S snapshots at once:
+//   K = 1/2 sum_i m_i |v_i|^2                                  metrics.py:86
+//   U = -1/2 G sum_{i != j} m_i m_j / sqrt(|x_i - x_j|^2 + eps^2)   metrics.py:90-102
+//   p = sum_i m_i v_i                                           metrics.py:131
+// One CTA per (trajectory, snapshot): the snapshot's positions and masses go to shared memory once, thread i sums the
+// pair terms of bodies i+1 .. i+N/2 (cyclically), so every unordered pair is evaluated ONCE and every thread does the
+// same work -- half the arithmetic of the row-wise form; for even N the pairs at distance N/2 would be met from both
+// ends and are taken by the lower-numbered end only.  Reduction order is fixed (thread-sequential, shuffle tree, warp order).
+// ------------------------------------------------------------------------------------------------------------------
+namespace nb {
+
+constexpr int kSnapEnergyMaxBodies = 4096;  // 4 doubles per body in shared memory (128 KB)
+
+// kF32Product: the masses are float32 and the reference forms m_i * m_j in float32 (np.outer of a float32 array,
+// metrics.py:82): the product is rounded the same way here, so the energies agree to float64 rounding, not 1e-8.
+template <bool kF32Product>
+__global__ void __launch_bounds__(256)
+snapshot_energy_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                       const void* __restrict__ masses, int masses_are_f32, int mass_stride, int S, int N, double G,
+                       double eps2, double* __restrict__ out) {
+    extern __shared__ __align__(16) double4 body[];  // x, y, z, m
+    __shared__ double red[5][8];
+    const int snap = blockIdx.x;                  // b * S + s
+    const int b = snap / S;
+    const double* x = pos + (size_t)snap * N * 3;
+    const double* v = vel + (size_t)snap * N * 3;
+    auto mass = [&](int i) {
+        const size_t mi = (size_t)b * mass_stride + i;
+        return masses_are_f32 ? (double)static_cast<const float*>(masses)[mi] : static_cast<const double*>(masses)[mi];
+    };
+    const bool potential = pos != nullptr;  // momentum / kinetic energy only (compute_momentum_error) when null
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        body[i] = potential ? make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], mass(i)) : make_double4(0., 0., 0., mass(i));
+    __syncthreads();
+    double k = 0.0, u = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+    const int half = N / 2;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double4 me = body[i];
+        const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
+        k += 0.5 * me.w * (vx * vx + vy * vy + vz * vz);
+        px += me.w * vx;
+        py += me.w * vy;
+        pz += me.w * vz;
+        // partners i+1 .. i+half (mod N); for even N the last one (distance N/2) is shared with the partner: the
+        // lower index takes it
+        const int cnt = !potential ? 0 : (N % 2 == 0 && i >= half) ? half - 1 : half;
+        double phi = 0.0;
+        int j = i + 1 < N ? i + 1 : 0;
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const double4 p = body[j];
+            const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
+            const double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
+            const double mm = kF32Product ? (double)((float)me.w * (float)p.w) : p.w;
+            phi += r2 > 0.0 ? mm * rsqrt_f64(r2) : 0.0;
+            j = j + 1 < N ? j + 1 : 0;
+        }
+        u -= kF32Product ? G * phi : G * me.w * phi;
+    }
+    double vals[5] = {k, u, px, py, pz};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        double s = vals[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        out[(size_t)snap * 5 + threadIdx.x] = s;
+    }
+}
+
+}  // namespace nb
+
+extern "C" {
+
+int nb_snapshot_energy_max_bodies(void) { return nb::kSnapEnergyMaxBodies; }
+
+int nb_snapshot_energy_f64(const double* pos, const double* vel, const void* masses, int masses_are_f32,
+                           int mass_stride, int B, int S, int N, double G, double softening, double* out,
+                           nb_stream_t s) {
+    NB_REQUIRE(vel && masses && out, "null pointer argument");  // pos may be null: K and p only, U = 0
+    NB_REQUIRE(B > 0 && S > 0 && N > 0 && N <= nb::kSnapEnergyMaxBodies, "need B, S > 0 and 0 < N <= %d (got %d %d %d)",
+               nb::kSnapEnergyMaxBodies, B, S, N);
+    NB_REQUIRE(mass_stride == 0 || mass_stride == N, "mass_stride must be 0 (shared) or N");
+    NB_REQUIRE((long long)B * S <= 0x7fffffffLL, "too many snapshots");
+    const size_t smem = (size_t)N * sizeof(double4);
+    auto kern = masses_are_f32 ? nb::snapshot_energy_kernel<true> : nb::snapshot_energy_kernel<false>;
+    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = nb::round_up(N < 256 ? N : 256, 32);
+    kern<<<B * S, threads, smem, (cudaStream_t)s>>>(pos, vel, masses, masses_are_f32, mass_stride, S, N, G,
+                                                    softening * softening, out);
+    return nb::check_launch("snapshot energy kernel");
+}
+
+}  // extern "C"

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "nb_copy_rows_d2h_async": (_ci, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "nb_energy_workspace_bytes": (_sz, [_ci, _ci]),
     "nb_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
+    "nb_snapshot_energy_max_bodies": (_ci, []),
+    "nb_snapshot_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _cd, _cd, _vp, _vp]),
     "nb_window_count": (_ci, [_ci, _ci, _ci]),
     "nb_window_gather_f32": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp]),
     "nbh_accel_direct": (_ci, [_vp, _vp, _ci, _ci, _cd, _ci, _vp]),
@@ -615,6 +617,34 @@ class Engine:
                                                       self._p(targets), self._stream()))
             self.launches += 1
         return inputs, targets
+
+    def snapshot_energies(self, pos_d, vel_d, m_d, masses_f32: int, mass_stride: int, softening: float,
+                          G: float = 6.67430e-11):
+        """K4b on device snapshot stacks (B, S, N, 3) float64 -> (B, S, 5) device tensor: K, U, px, py, pz of every
+        snapshot (reference src/utils/metrics.py:62-137 for B trajectories at once).  One launch."""
+        torch = _torch()
+        ok = vel_d.dim() == 4 and vel_d.shape[3] == 3 and vel_d.dtype == torch.float64 and vel_d.is_contiguous()
+        if pos_d is not None:
+            ok = ok and tuple(pos_d.shape) == tuple(vel_d.shape) and pos_d.dtype == torch.float64 and pos_d.is_contiguous()
+        if not ok:
+            raise ValueError("snapshot_energies needs contiguous float64 (B, S, N, 3) position and velocity stacks")
+        B, S, N = int(vel_d.shape[0]), int(vel_d.shape[1]), int(vel_d.shape[2])
+        out = torch.empty((B, S, 5), dtype=torch.float64, device=self.device)
+        if N > int(self.lib.nb_snapshot_energy_max_bodies()) and pos_d is not None:
+            # large systems: each state fills the GPU on its own (K4), one after the other
+            for b in range(B):
+                mb = m_d if mass_stride == 0 else m_d[b]
+                for s_ in range(S):
+                    out[b, s_, :2] = self.energy_slab(pos_d[b, s_], vel_d[b, s_], mb, masses_f32, N, 0, N, softening)
+                    out[b, s_, 2:] = (mb.to(torch.float64)[:, None] * vel_d[b, s_]).sum(dim=0)
+            if G != 6.67430e-11:
+                out[:, :, 1] *= G / 6.67430e-11
+            return out
+        self._check(self.lib.nb_snapshot_energy_f64(self._p(pos_d), self._p(vel_d), self._p(m_d), masses_f32,
+                                                    mass_stride, B, S, N, float(G), float(softening), self._p(out),
+                                                    self._stream()))
+        self.launches += 1
+        return out
 
     def energy_slab(self, pos_d, vel_d, m_d, masses_f32: int, n: int, i0: int, n_i: int, softening: float):
         torch = _torch()

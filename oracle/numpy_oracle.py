@@ -66,3 +66,28 @@ def sliding_windows(positions, velocities, n_states: int, sequence_length: int, 
     if not ins:
         return np.zeros((0, sequence_length, n, 6), np.float32), np.zeros((0, n, 6), np.float32)
     return np.stack(ins), np.stack(tgs)
+
+
+def snapshot_energies(positions, velocities, masses, G: float = 6.67430e-11, softening: float = SOFTENING):
+    """compute_energy_error / compute_momentum_error of the reference, src/utils/metrics.py:62-137, restated per
+    snapshot without the N x N x 3 temporary: for every stored step t
+        K_t = 1/2 sum_i m_i |v_i|^2                                   (:86)
+        U_t = -1/2 G sum_{i != j} m_i m_j / sqrt(|x_i - x_j|^2 + eps^2)   (:90-102)
+        p_t = sum_i m_i v_i                                           (:131)
+    positions, velocities (S, N, 3); masses (N,).  Returns (K (S,), U (S,), p (S, 3))."""
+    pos = np.asarray(positions, dtype=np.float64)
+    vel = np.asarray(velocities, dtype=np.float64)
+    m = np.asarray(masses)          # dtype kept: np.outer(masses, masses) (:82) rounds the products of float32 masses
+    S, N = pos.shape[0], pos.shape[1]                                                     # to float32
+    K, U, P = np.zeros(S), np.zeros(S), np.zeros((S, 3))
+    for t in range(S):
+        K[t] = 0.5 * np.sum(m * np.sum(vel[t] ** 2, axis=1))
+        P[t] = np.sum(m[:, None] * vel[t], axis=0)
+        u = 0.0
+        for i in range(N):
+            d = pos[t] - pos[t, i]
+            inv_r = 1.0 / np.sqrt(np.sum(d * d, axis=1) + softening ** 2)
+            inv_r[i] = 0.0                                            # np.fill_diagonal(inv_r, 0), :98
+            u += np.sum((m[i] * m) * inv_r)                           # row i of m_matrix * inv_r, :102
+        U[t] = -0.5 * G * u
+    return K, U, P
