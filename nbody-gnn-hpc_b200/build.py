@@ -47,12 +47,15 @@ def stale() -> bool:
     return LIB.stat().st_mtime < newest
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: Path = None) -> Path:
+    """extra_flags / out: experiment builds (e.g. -DNB_F64_PAIR_FIRST_ORDER) into another file; the default build is
+    what everything loads (NBODY_B200_LIB selects another library at run time)."""
+    if out is None and not extra_flags and not force and not stale():
         return LIB
     nvcc = _nvcc()
     LIBDIR.mkdir(exist_ok=True)
-    objdir = LIBDIR / "obj"
+    lib_out = Path(out) if out is not None else LIB
+    objdir = LIBDIR / ("obj" if out is None else "obj_" + lib_out.stem)
     objdir.mkdir(exist_ok=True)
     log = []
     objs = []
@@ -62,30 +65,32 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in sources():
         obj = objdir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *ccbin, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *ccbin, "-c", str(src), "-o", str(obj)]
         procs.append((src, obj, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)))
     for src, obj, cmd, p in procs:
-        out, _ = p.communicate()
-        log.append("$ " + " ".join(cmd) + "\n" + out)
+        text, _ = p.communicate()
+        log.append("$ " + " ".join(cmd) + "\n" + text)
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
             raise RuntimeError(f"nvcc failed on {src.name}")
         objs.append(str(obj))
-    cmd = [nvcc, "-shared", *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs]
+    cmd = [nvcc, "-shared", *ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib_out), *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     log.append("$ " + " ".join(cmd) + "\n" + r.stdout)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    (LIBDIR / "ptxas.log").write_text("\n".join(log))
+    (LIBDIR / ("ptxas.log" if out is None else f"ptxas_{lib_out.stem}.log")).write_text("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--out", default=None, help="experiment build: write the library here")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="experiment build: extra -D macro")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, extra_flags=[f"-D{d}" for d in a.defines], out=a.out))

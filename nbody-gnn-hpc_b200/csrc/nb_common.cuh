@@ -119,9 +119,28 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 //   y0 = seed(r2),  e = 1 - r2*y0^2  (one FMA on the rounded square),  r2^(-3/2) = y0^3 * (1 + 3/2 e + 15/8 e^2 + O(e^3)),
 // i.e. one third-order correction of the cubed seed: truncation 35/16 e^3 < 2^-64 for |e| < 2^-21.
 // 16 FP64-pipe operations + 1 MUFU per interaction.
+//
+// Build option -DNB_F64_PAIR_FIRST_ORDER (tools/probe_f64_variants.py measures it): first-order correction with the
+// mass folded into the polynomial -- r2^(-3/2) G m ~ y0^3 (c0 + c1 p), p = r2 y0^2, c0 = 5/2 G m, c1 = -3/2 G m; the
+// stream's mass slot then holds c0 and c1 = -0.6 c0 -- 14 operations (K3, c1 kept in shared memory) or 14.5 (K1/K2,
+// c1 formed once per j).  Measured: 4.88 ms against 5.27 ms for the 300x200x400 ensemble, 3.81 against 4.15 ms per
+// N = 65,536 evaluation.  Truncation 15/8 e^2 < 5e-13 relative, same sign for every pair: inside the 1e-10 bar, but on
+// the reference's chaotic default initial conditions (e-folding ~11 steps) that is amplified to 1e-8 .. 1e-3 in the
+// positions within 50 steps -- three orders of magnitude above the reference's own reordering noise, with 43 % instead
+// of 97 % of the 300 data-generation systems still inside 1e-8 of the CPU restatement at step 50 (measured).  So it is an
+// option for well-conditioned systems, not the default.  (A second-order polynomial with three folded constants per
+// body -- 15 operations, 48-byte stream records -- was built and measured too: no faster than the 16-operation form
+// below on either kernel, the extra shared-memory load per j costs what the saved operation gains.)
+#ifdef NB_F64_PAIR_FIRST_ORDER
+constexpr double kMassSlotF64 = 2.5;   // stream slot 3 of the f64 layout = kMassSlotF64 * G * m  (c0)
+constexpr double kC1OverC0 = -0.6;     // c1 = -3/2 G m = -0.6 c0
+#else
+constexpr double kMassSlotF64 = 1.0;
+constexpr double kC1OverC0 = 0.0;
+#endif
 template <bool kZeroEps>
 __device__ __forceinline__ void pair_f64(double xi, double yi, double zi, double xj, double yj, double zj, double gmj,
-                                         double eps2, double& ax, double& ay, double& az) {
+                                         double c1j, double eps2, double& ax, double& ay, double& az) {
     const double dx = xj - xi;
     const double dy = yj - yi;
     const double dz = zj - zi;
@@ -130,6 +149,20 @@ __device__ __forceinline__ void pair_f64(double xi, double yi, double zi, double
     r2 = fma(dz, dz, r2);
     double y0 = rsqrt_seed(r2);
     if (kZeroEps) y0 = (r2 > 0.0) ? y0 : 0.0;  // eps == 0: the i == j term (and exact overlaps) contribute 0
+#ifdef NB_F64_PAIR_FIRST_ORDER
+    {
+        const double s = y0 * y0;
+        const double pp = r2 * s;
+        const double c = fma(c1j, pp, gmj);  // gmj is c0 here
+        const double t = y0 * s;
+        const double f1 = t * c;
+        ax = fma(f1, dx, ax);
+        ay = fma(f1, dy, ay);
+        az = fma(f1, dz, az);
+        return;
+    }
+#endif
+    (void)c1j;
     const double y2 = y0 * y0;
     const double e = fma(-r2, y2, 1.0);  // y2 carries one rounding (2^-53): 1.5 * 2^-53 relative in f
     const double g = gmj * y0;

@@ -65,14 +65,19 @@ namespace nb {
 
 namespace cg = cooperative_groups;
 
+// The mass slot of a body (pos.w): G m -- or, in the first-order float64 build (nb_common.cuh), c0 = 5/2 G m with
+// the companion constant c1 = -0.6 c0 kept in the lane's c1[] array.
+__device__ __forceinline__ double mass_slot(double gm, double*) { return kMassSlotF64 * gm; }
+__device__ __forceinline__ float mass_slot(double gm, float*) { return (float)gm; }
+
 template <bool kZeroEps>
 __device__ __forceinline__ void pair_any(double xi, double yi, double zi, double xj, double yj, double zj, double gmj,
-                                         double eps2, double& ax, double& ay, double& az) {
-    pair_f64<kZeroEps>(xi, yi, zi, xj, yj, zj, gmj, eps2, ax, ay, az);
+                                         double c1j, double eps2, double& ax, double& ay, double& az) {
+    pair_f64<kZeroEps>(xi, yi, zi, xj, yj, zj, gmj, c1j, eps2, ax, ay, az);
 }
 template <bool kZeroEps>
 __device__ __forceinline__ void pair_any(float xi, float yi, float zi, float xj, float yj, float zj, float gmj,
-                                         float eps2, float& ax, float& ay, float& az) {
+                                         float /*c1j*/, float eps2, float& ax, float& ay, float& az) {
     const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
     float r2 = fmaf(dx, dx, eps2);
     r2 = fmaf(dy, dy, r2);
@@ -118,9 +123,16 @@ struct EnsembleArgs {
     int* progress;    // per-system flag, zero on entry: 1 once the head steps of a shared system are parked
 };
 
+#ifdef NB_F64_PAIR_FIRST_ORDER
+constexpr int kC1Slots = 1;  // one more array of N per lane: c1[j]
+#else
+constexpr int kC1Slots = 0;
+#endif
+
 template <typename T>
 struct SystemSmem {
     typename Vec4<T>::type* pos;
+    T* c1;  // first-order float64 build only
     T* vel;
     T* acc;
     T* part;
@@ -129,7 +141,7 @@ struct SystemSmem {
 // shared memory of one lane, rounded to 16 bytes
 template <typename T>
 __host__ __device__ inline size_t lane_smem_bytes(int N, int parts) {
-    const size_t b = (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(2 + parts) * 3 * N * sizeof(T);
+    const size_t b = (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)((2 + parts) * 3 + kC1Slots) * N * sizeof(T);
     return (b + 15) / 16 * 16;
 }
 
@@ -259,7 +271,9 @@ __device__ __forceinline__ void load_piece(const EnsembleArgs& g, const Piece& p
         const size_t mi = (size_t)p.b * g.mass_stride + i;
         const double m = g.masses_are_f32 ? (double)static_cast<const float*>(g.masses)[mi]
                                           : static_cast<const double*>(g.masses)[mi];
-        pos_s[4 * i + 3] = (T)(kG * m);  // G * masses[j], nbody.py:57
+        const T slot = mass_slot(kG * m, (T*)nullptr);  // G * masses[j], nbody.py:57
+        pos_s[4 * i + 3] = slot;
+        if (kC1Slots) s.c1[i] = slot * (T)kC1OverC0;
     }
 }
 
@@ -301,8 +315,9 @@ __device__ __forceinline__ void force_phase(const EnsembleArgs& g, const SystemS
 #pragma unroll 8
     for (int j = jb; j < je; ++j) {
         const V4 pj = s.pos[j];
-        pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, eps2, ax0, ay0, az0);
-        pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, eps2, ax1, ay1, az1);
+        const T c1 = kC1Slots ? s.c1[j] : T(0);
+        pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, c1, eps2, ax0, ay0, az0);
+        pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, c1, eps2, ax1, ay1, az1);
     }
     T* pa = s.part + (size_t)q * n3;
     pa[3 * i0 + 0] = ax0; pa[3 * i0 + 1] = ay0; pa[3 * i0 + 2] = az0;
@@ -392,7 +407,8 @@ ensemble_kernel(const EnsembleArgs g) {
     for (int L = 0; L < kMaxLanes; ++L) {
         char* base = smem + (size_t)L * lane_smem_bytes<T>(N, parts);
         sm[L].pos = reinterpret_cast<V4*>(base);
-        sm[L].vel = reinterpret_cast<T*>(base + (size_t)N * sizeof(V4));
+        sm[L].c1 = reinterpret_cast<T*>(base + (size_t)N * sizeof(V4));
+        sm[L].vel = sm[L].c1 + kC1Slots * N;
         sm[L].acc = sm[L].vel + n3;
         sm[L].part = sm[L].acc + n3;
         active[L] = false;
@@ -474,7 +490,8 @@ constexpr int kClusterCtas = 8;  // the portable maximum; the launch may use 4 o
 template <typename T>
 __host__ __device__ inline size_t cluster_smem_bytes(int N, int parts, int C) {
     const int S = (N + C - 1) / C;
-    return 2 * (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)(parts + 2) * 3 * S * sizeof(T);
+    return 2 * (size_t)N * sizeof(typename Vec4<T>::type) + (size_t)kC1Slots * N * sizeof(T) +
+           (size_t)(parts + 2) * 3 * S * sizeof(T);
 }
 
 // --- distributed shared memory with transaction counting ----------------------------------------------------------
@@ -513,7 +530,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const 
     const int i_lo = min(N, rank * S), ns = min(N, i_lo + S) - i_lo;
     const int tid = threadIdx.x;
     V4* const pos0 = reinterpret_cast<V4*>(smem);              // buffer c is pos0 + c * N
-    T* part = reinterpret_cast<T*>(pos0 + 2 * N);               // parts x 3S
+    T* c1s = reinterpret_cast<T*>(pos0 + 2 * N);                // N, first-order float64 build only
+    T* part = c1s + kC1Slots * N;                               // parts x 3S
     T* vel = part + (size_t)parts * 3 * S;                      // 3S, (body, component) order
     T* acc = vel + 3 * S;
     // every CTA's copy of the two position buffers, as seen from here (distributed shared memory)
@@ -550,9 +568,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const 
             const size_t mi = (size_t)b * g.mass_stride + i;
             const double m = g.masses_are_f32 ? (double)static_cast<const float*>(g.masses)[mi]
                                               : static_cast<const double*>(g.masses)[mi];
-            const T gm = (T)(kG * m);  // G * masses[j], nbody.py:57
+            const T gm = mass_slot(kG * m, (T*)nullptr);  // G * masses[j], nbody.py:57
             reinterpret_cast<T*>(pos0)[4 * i + 3] = gm;
             reinterpret_cast<T*>(pos0 + N)[4 * i + 3] = gm;
+            if (kC1Slots) c1s[i] = gm * (T)kC1OverC0;
         }
         for (int idx = tid; idx < 3 * ns; idx += blockDim.x) {
             vel[idx] = (T)__ldcg(&g.v[sbase + 3 * i_lo + idx]);
@@ -586,7 +605,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const 
 #pragma unroll 20
                     for (int j = jb; j < je; ++j) {
                         const V4 pj = pos[j];
-                        pair_any<kZeroEps>(me.x, me.y, me.z, pj.x, pj.y, pj.z, pj.w, eps2, ax, ay, az);
+                        pair_any<kZeroEps>(me.x, me.y, me.z, pj.x, pj.y, pj.z, pj.w, kC1Slots ? c1s[j] : T(0), eps2, ax,
+                                           ay, az);
                     }
                     T* pa = part + (size_t)q * 3 * S + 3 * li_f;
                     pa[0] = ax; pa[1] = ay; pa[2] = az;

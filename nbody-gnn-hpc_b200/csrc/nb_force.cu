@@ -428,9 +428,10 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
         for (int j = 0; j < n_j; ++j) {
             const double2 a = t[2 * j];      // x y
             const double2 b = t[2 * j + 1];  // z gm
+            const double c1 = b.y * kC1OverC0;  // first-order build only (dead code otherwise): once per j
 #pragma unroll
             for (int k = 0; k < kP; ++k)
-                pair_f64<kZeroEps>(xi[k], yi[k], zi[k], a.x, a.y, b.x, b.y, eps2, ax[k], ay[k], az[k]);
+                pair_f64<kZeroEps>(xi[k], yi[k], zi[k], a.x, a.y, b.x, b.y, c1, eps2, ax[k], ay[k], az[k]);
         }
     };
     stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 32, (j1 - j0) * 32, ring, bars, consume);
@@ -483,6 +484,7 @@ pack_kernel(const double* __restrict__ pos, const void* __restrict__ masses, int
         const double m = masses_are_f32 ? (double)static_cast<const float*>(masses)[i]
                                         : static_cast<const double*>(masses)[i];
         gm = kG * m;  // G * masses[j], nbody.py:57
+        if (sizeof(T) == 8) gm *= kMassSlotF64;  // 1 unless the first-order f64 pair is built (nb_common.cuh)
     }
     StreamIO<T>::put(stream, i, 0, (T)x);
     StreamIO<T>::put(stream, i, 1, (T)y);
