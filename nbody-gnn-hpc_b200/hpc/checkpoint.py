@@ -58,78 +58,95 @@ def _read_metadata(f) -> Dict:
     return out
 
 
+def _split_state(state: Dict):
+    """A state dict's entries by how the file formats store them: arrays (datasets) and plain numbers (attributes).
+    Anything else (strings, nested objects) has no place in either format and is left out, as in the reference."""
+    arrays = {k: v for k, v in state.items() if isinstance(v, np.ndarray)}
+    numbers = {k: v for k, v in state.items() if isinstance(v, (int, float)) and not isinstance(v, bool)}
+    return arrays, numbers
+
+
+class _Hdf5States:
+    """``{name}.h5``: one gzip dataset per array, one root attribute per number, attribute ``created_at``,
+    optional group ``metadata`` (format of reference checkpoint.py:44-70,118-142)."""
+    suffix = ".h5"
+
+    @staticmethod
+    def write(path: Path, state: Dict, metadata: Optional[Dict]) -> None:
+        arrays, numbers = _split_state(state)
+        with _h5py().File(path, 'w') as f:
+            for key, arr in arrays.items():
+                f.create_dataset(key, data=arr, compression='gzip')
+            for key, value in numbers.items():
+                f.attrs[key] = value
+            _write_metadata(f, metadata)
+            f.attrs['created_at'] = datetime.now().isoformat()
+
+    @staticmethod
+    def read(path: Path) -> Dict:
+        with _h5py().File(path, 'r') as f:
+            state = {key: f[key][:] for key in f.keys() if key != 'metadata'}
+            state.update({key: f.attrs[key] for key in f.attrs.keys() if key != 'created_at'})
+            if 'metadata' in f:
+                state['metadata'] = _read_metadata(f)
+        return state
+
+
+class _NpzStates:
+    """``{name}.npz``: arrays under their own names, numbers as 0-d arrays named ``scalar_<key>``, the metadata dict
+    as one JSON string ``metadata_json`` (format of reference checkpoint.py:72-106,144-170)."""
+    suffix = ".npz"
+    _NUMBER, _META = "scalar_", "metadata_json"
+
+    @classmethod
+    def write(cls, path: Path, state: Dict, metadata: Optional[Dict]) -> None:
+        arrays, numbers = _split_state(state)
+        payload = dict(arrays)
+        payload.update({cls._NUMBER + k: np.array(v) for k, v in numbers.items()})
+        if metadata:
+            payload[cls._META] = np.array(json.dumps(metadata))
+        np.savez_compressed(path, **payload)
+
+    @classmethod
+    def read(cls, path: Path) -> Dict:
+        state = {}
+        with np.load(path, allow_pickle=True) as data:
+            for key in data.files:
+                if key == cls._META:
+                    state['metadata'] = json.loads(str(data[key]))
+                elif key.startswith(cls._NUMBER):
+                    state[key[len(cls._NUMBER):]] = data[key].item()
+                else:
+                    state[key] = data[key]
+        return state
+
+
 class CheckpointManager:
-    """Saves and loads simulation states and trajectories (reference checkpoint.py:19-299)."""
+    """Saves and loads simulation states and trajectories (public surface of reference checkpoint.py:19-299)."""
+
+    _STATE_FORMATS = {"hdf5": _Hdf5States, "npz": _NpzStates}
+    _TRAJECTORY_SUFFIX = "_trajectory.h5"
 
     def __init__(self, checkpoint_dir: str = "./data/checkpoints", format: str = "hdf5"):
         self.checkpoint_dir = Path(checkpoint_dir)
         self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
         self.format = format
 
-    # ---- single states -------------------------------------------------------------------------
+    # ---- single states (not on the engine's path; kept because the class is public API) ----------
     def save_state(self, state: Dict, name: str, metadata: Optional[Dict] = None) -> str:
-        """Save one state dict (reference :44-106)."""
-        if self.format == "hdf5":
-            return self._save_hdf5(state, name, metadata)
-        return self._save_npz(state, name, metadata)
-
-    def _save_hdf5(self, state: Dict, name: str, metadata: Optional[Dict]) -> str:
-        filepath = self.checkpoint_dir / f"{name}.h5"
-        with _h5py().File(filepath, 'w') as f:
-            for key, value in state.items():
-                if isinstance(value, np.ndarray):
-                    f.create_dataset(key, data=value, compression='gzip')
-                elif isinstance(value, (int, float)):
-                    f.attrs[key] = value
-            _write_metadata(f, metadata)
-            f.attrs['created_at'] = datetime.now().isoformat()
-        return str(filepath)
-
-    def _save_npz(self, state: Dict, name: str, metadata: Optional[Dict]) -> str:
-        filepath = self.checkpoint_dir / f"{name}.npz"
-        arrays = {k: v for k, v in state.items() if isinstance(v, np.ndarray)}
-        for k, v in state.items():
-            if isinstance(v, (int, float)) and not isinstance(v, bool):
-                arrays[f"scalar_{k}"] = np.array(v)
-        if metadata:
-            arrays['metadata_json'] = np.array(json.dumps(metadata))
-        np.savez_compressed(filepath, **arrays)
-        return str(filepath)
+        """Save one state dict in the manager's format; returns the file path."""
+        codec = self._STATE_FORMATS.get(self.format, _NpzStates)       # anything but "hdf5" means npz, as upstream
+        path = self.checkpoint_dir / (name + codec.suffix)
+        codec.write(path, state, metadata)
+        return str(path)
 
     def load_state(self, name: str) -> Dict:
-        """Load a state saved by save_state: HDF5 first, then npz (reference :108-170)."""
-        hdf5_path = self.checkpoint_dir / f"{name}.h5"
-        if hdf5_path.exists():
-            return self._load_hdf5(hdf5_path)
-        npz_path = self.checkpoint_dir / f"{name}.npz"
-        if npz_path.exists():
-            return self._load_npz(npz_path)
+        """Load a state saved by save_state, whichever format it is in (HDF5 looked for first)."""
+        for codec in (_Hdf5States, _NpzStates):
+            path = self.checkpoint_dir / (name + codec.suffix)
+            if path.exists():
+                return codec.read(path)
         raise FileNotFoundError(f"Checkpoint '{name}' not found")
-
-    def _load_hdf5(self, filepath: Path) -> Dict:
-        state = {}
-        with _h5py().File(filepath, 'r') as f:
-            for key in f.keys():
-                if key != 'metadata':
-                    state[key] = f[key][:]
-            for key in f.attrs.keys():
-                if key != 'created_at':
-                    state[key] = f.attrs[key]
-            if 'metadata' in f:
-                state['metadata'] = _read_metadata(f)
-        return state
-
-    def _load_npz(self, filepath: Path) -> Dict:
-        data = np.load(filepath, allow_pickle=True)
-        state = {}
-        for key in data.files:
-            if key.startswith('scalar_'):
-                state[key[7:]] = data[key].item()
-            elif key == 'metadata_json':
-                state['metadata'] = json.loads(str(data[key]))
-            else:
-                state[key] = data[key]
-        return state
 
     # ---- trajectories ----------------------------------------------------------------------------
     def save_trajectory_arrays(self, name: str, positions: np.ndarray, velocities: np.ndarray,
@@ -179,25 +196,24 @@ class CheckpointManager:
         return trajectory
 
     def list_checkpoints(self) -> List[str]:
-        """Names of all checkpoint files, trajectories marked (reference :275-284)."""
-        names = []
-        for f in self.checkpoint_dir.iterdir():
-            if f.suffix in ('.h5', '.npz'):
-                names.append(f.stem.replace('_trajectory', ' (trajectory)'))
-        return sorted(names)
+        """Sorted names of everything stored here; trajectory files are listed as ``<name> (trajectory)``."""
+        tag = self._TRAJECTORY_SUFFIX[:-len(".h5")]
+        stored = [p.stem for p in self.checkpoint_dir.iterdir() if p.suffix in (".h5", ".npz")]
+        return sorted(stem.replace(tag, " (trajectory)") for stem in stored)
 
     def trajectory_exists(self, name: str) -> bool:
         """Resume check used by generate_data.py:128 (reference :286-289)."""
-        return (self.checkpoint_dir / f"{name}_trajectory.h5").exists()
+        return (self.checkpoint_dir / (name + self._TRAJECTORY_SUFFIX)).exists()
 
     def delete_checkpoint(self, name: str) -> bool:
-        """Delete the first matching file of a checkpoint name (reference :292-299)."""
-        for ext in ('.h5', '.npz', '_trajectory.h5'):
-            filepath = self.checkpoint_dir / f"{name}{ext}"
-            if filepath.exists():
-                filepath.unlink()
-                return True
-        return False
+        """Remove ONE file stored under this name -- a state (.h5, then .npz) before a trajectory -- and say whether
+        there was one."""
+        candidates = [self.checkpoint_dir / (name + sfx) for sfx in (".h5", ".npz", self._TRAJECTORY_SUFFIX)]
+        victim = next((p for p in candidates if p.exists()), None)
+        if victim is None:
+            return False
+        victim.unlink()
+        return True
 
 
 def sliding_windows(positions: np.ndarray, velocities: np.ndarray, n_steps: int, sequence_length: int,

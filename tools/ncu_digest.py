@@ -68,8 +68,21 @@ def main():
     summary = ROOT / "profiles" / "summary.json"
     merged = json.loads(summary.read_text()) if summary.exists() else {}
     merged.update(digest)  # kernels of other captures are kept
+    # the sources these captures were taken on: bench.py compares it with the sources it runs (roofline.traffic_stale)
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "nbody-gnn-hpc_b200" / "csrc").glob("*.cu*")) + [ROOT / "include" / "nbody_b200.h"]:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    merged["_source_hash"] = h.hexdigest()[:16]
+    try:
+        merged["_git_head"] = subprocess.run(["git", "-C", str(ROOT), "rev-parse", "--short", "HEAD"],
+                                             stdout=subprocess.PIPE, text=True).stdout.strip()
+    except Exception:
+        pass
     summary.write_text(json.dumps(merged, indent=1) + "\n")
     print(json.dumps({k: (round(v["duration_ms"], 3), round(v["pipe_fp64_pct"] or v["pipe_fma_pct"], 1)) for k, v in digest.items()}))
+    print("source hash", merged["_source_hash"], "(re-digest ALL kernels' captures after any change to csrc/)")
 
 
 if __name__ == "__main__":

@@ -64,4 +64,35 @@ if "energy" in which:
     for _ in range(2):
         eng.energy_slab(pos_d, vel_d, m_d, f32, n, 0, n, 0.01)
     torch.cuda.synchronize()
+if "snap" in which:
+    # K4b on the stacks of a 300 x 401 x 200 ensemble
+    B, S, N = 300, 401, 200
+    g = torch.Generator(device=eng.device).manual_seed(2)
+    pos = torch.randn((B, S, N, 3), dtype=torch.float64, device=eng.device, generator=g)
+    vel = torch.randn((B, S, N, 3), dtype=torch.float64, device=eng.device, generator=g)
+    m_d, f32 = eng._masses_dev(ics.shared_masses(N, 42))
+    for _ in range(2):
+        eng.snapshot_energies(pos, vel, m_d, f32, 0, 1e-9)
+    torch.cuda.synchronize()
+if "peer" in which:
+    # the fused force + leapfrog + peer-store step kernel, one rank that is its own peer, N = 65,536 float32
+    from hpc.sharded import slab_bounds  # noqa: F401
+    n = 65536
+    x, v, m = ics.plummer_ic(n, seed=7)
+    pos_d = eng.to_device(x)
+    m_d, f32 = eng._masses_dev(m)
+    cur = eng.pack(pos_d, m_d, f32, n, np.float32)
+    nxt = cur.clone()
+    vel = eng.to_device(v, torch.float32)
+    ws = eng.workspace(n, n, np.float32)
+    acc = eng.accel_slab(cur, n, 0, n, 1e-3, ws)
+    flags = torch.zeros(16, dtype=torch.int32, device=eng.device)
+    eng.kick_drift_slab(cur, nxt, vel, acc, n, 0, n, 1e-3)
+    cur, nxt = nxt, cur
+    for k in range(1, 4):
+        eng.step_peer_slab(cur, [nxt.data_ptr()], [flags.data_ptr()], 0, 0, k, vel, acc, n, 0, n, 1e-3, 1e-3,
+                           _cuda.NB_STEP_CONTINUE | _cuda.NB_STEP_PEER_SYNC, None, None, None, ws)
+        cur, nxt = nxt, cur
+    torch.cuda.synchronize()
+    eng.step_status(ws, n)
 print("ok")
