@@ -42,6 +42,7 @@ extern "C" {
 /* phases recorded in the workspace's error word by nb_step_peer_* (low byte; the lost rank is above it) */
 #define NB_PEER_LOST_BEFORE_FORCE 1   /* wait_seq never reached: the force pass did not run */
 #define NB_PEER_LOST_AFTER_STEP 2     /* NB_STEP_PEER_SYNC: signal_seq of that rank never seen */
+#define NB_PERSIST_STALLED 3          /* nb_run_* one-launch kernel: a grid barrier never completed */
 
 /* nb_step_* flags */
 #define NB_STEP_CONTINUE 1    /* after the closing kick, also do the next step's opening kick + drift */
@@ -158,6 +159,10 @@ int nb_step_status(const void* workspace, int n, nb_stream_t s);
  * (v_0, a_0) on entry and (v_n, a_n) on return.  Snapshot s (s = 1..n_steps/save_interval) of the
  * state after step s*save_interval goes to row block s of snap_* ((n_snap, n, 3) float64, n_snap =
  * 1 + n_steps/save_interval); row block 0 (the initial state) is written here too. */
+/* Systems of at most nb_persist_max_bodies() bodies run ALL their steps in one cooperative launch (K2p,
+ * csrc/nb_persist.cu: warp-tasks on a persistent grid, one grid barrier per step) -- bit-identical to the per-step
+ * launches, which environment NB_NO_PERSIST=1 selects; nb_step_status(workspace) reports a stalled launch. */
+int nb_persist_max_bodies(void);
 int nb_run_f64(double* stream_a, double* stream_b, double* vel, double* acc, int n, double dt,
                double softening, int n_steps, int save_interval,
                double* snap_pos, double* snap_vel, double* snap_acc,

@@ -52,6 +52,12 @@ static inline size_t ws_header_bytes(int n) {
     return (((size_t)(n > 0 ? n : 1) / 128 + 3) * sizeof(int) + 255) / 256 * 256;
 }
 
+// Behind the partials of a WHOLE-system workspace (n_i == n): the persistent multi-step kernel's words -- the grid
+// barrier and one arrival counter per group of 32 bodies (nb_persist.cu).
+static inline size_t ws_persist_bytes(int n) {
+    return (((size_t)(n > 0 ? n : 1) / 32 + 8) * sizeof(int) + 255) / 256 * 256;
+}
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

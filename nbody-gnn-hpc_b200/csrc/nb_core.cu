@@ -81,6 +81,7 @@ size_t nb_workspace_bytes(int n, int n_i, int is_f64) {
     // header: one arrival counter per i-tile of the WHOLE system (smallest tile: 128 bodies), so the layout does not
     // depend on the slab; must be zero before the first launch that uses the workspace -- every launch leaves it zero
     bytes += nb::ws_header_bytes(n);
+    if (n_i == n) bytes += nb::ws_persist_bytes(n);  // whole-system runs may take the one-launch kernel (nb_persist.cu)
     return bytes;
 }
 

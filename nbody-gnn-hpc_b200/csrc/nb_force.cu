@@ -23,7 +23,7 @@
 
 #include <type_traits>
 
-#include "nb_common.cuh"
+#include "nb_tiles.cuh"
 
 namespace nb {
 
@@ -151,23 +151,6 @@ __device__ __forceinline__ float f32_stream_coord(const float* __restrict__ stre
 // ------------------------------------------------------------------------------------------------
 // stream access and the per-body finish (ordered segment reduction + leapfrog)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-struct StreamIO;
-template <>
-struct StreamIO<double> {
-    static __device__ __forceinline__ double get(const double* s, int body, int c) { return s[(size_t)body * 4 + c]; }
-    static __device__ __forceinline__ void put(double* s, int body, int c, double v) { s[(size_t)body * 4 + c] = v; }
-};
-template <>
-struct StreamIO<float> {
-    static __device__ __forceinline__ float get(const float* s, int body, int c) {
-        return s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)];
-    }
-    static __device__ __forceinline__ void put(float* s, int body, int c, float v) {
-        s[(size_t)(body >> 1) * 8 + 2 * c + (body & 1)] = v;
-    }
-};
-
 enum { kEpiNone = 0, kEpiAccel = 1, kEpiStep = 2, kEpiStepPeer = 3 };
 
 // What the LAST CTA to finish an i-tile does with the tile's bodies, inside the force kernel itself.
@@ -330,52 +313,14 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
         zi[k] = f32_stream_coord(stream, gi, 2);
         ax[k] = ay[k] = az[k] = make_float2(0.f, 0.f);
     }
-    const float2 e2 = make_float2(eps2, eps2);
-
-    // The i == j term has r2 == eps2 and must contribute exactly 0 (the reference skips it, nbody.py:46).  dx = 0 is
-    // not enough: with eps = 1e-9, G*m*inv^3 overflows float32 for G*m > 3.4e11 (any star) and inf * 0 = NaN.  Testing
-    // every pair costs two ALU instructions per lane -- measured: 72 % -> 63 % of the FP32 peak at N = 65,536 -- so the
-    // test (r2 > eps2 ? inv : 0) is compiled only into a second copy of the loop, taken for the few j tiles that
-    // overlap this CTA's own bodies (a CTA-uniform branch per 4 KB tile).  eps == 0 needs nothing more: the same test
-    // removes r2 == 0.
+    // tiles that overlap this CTA's own bodies take the guarded copy of the loop (nb_tiles.cuh, f32_pairs)
     const int own_lo = i0 + blockIdx.x * (kBlock * kP), own_hi = min(own_lo + kBlock * kP, i0 + n_i);
-    auto tile_loop = [&](const float4* __restrict__ t, int n_pairs, auto guard) {
-#pragma unroll 2
-        for (int jp = 0; jp < n_pairs; ++jp) {
-            const float4 A = t[2 * jp];      // x0 x1 y0 y1
-            const float4 B = t[2 * jp + 1];  // z0 z1 gm0 gm1
-            const float2 xj = make_float2(A.x, A.y), yj = make_float2(A.z, A.w);
-            const float2 zj = make_float2(B.x, B.y), gj = make_float2(B.z, B.w);
-#pragma unroll
-            for (int k = 0; k < kP; ++k) {
-                const float2 dx = __fadd2_rn(xj, make_float2(-xi[k], -xi[k]));
-                const float2 dy = __fadd2_rn(yj, make_float2(-yi[k], -yi[k]));
-                const float2 dz = __fadd2_rn(zj, make_float2(-zi[k], -zi[k]));
-                float2 r2 = __ffma2_rn(dx, dx, e2);
-                r2 = __ffma2_rn(dy, dy, r2);
-                r2 = __ffma2_rn(dz, dz, r2);
-                float2 inv;
-                inv.x = rsqrt_approx(r2.x);
-                inv.y = rsqrt_approx(r2.y);
-                if (decltype(guard)::value) {
-                    inv.x = (r2.x > eps2) ? inv.x : 0.f;
-                    inv.y = (r2.y > eps2) ? inv.y : 0.f;
-                }
-                const float2 inv2 = __fmul2_rn(inv, inv);
-                float2 f = __fmul2_rn(gj, inv);
-                f = __fmul2_rn(f, inv2);
-                ax[k] = __ffma2_rn(f, dx, ax[k]);
-                ay[k] = __ffma2_rn(f, dy, ay[k]);
-                az[k] = __ffma2_rn(f, dz, az[k]);
-            }
-        }
-    };
     auto consume = [&](const char* tile, int bytes, int tile_index) {
         const float4* __restrict__ t = reinterpret_cast<const float4*>(tile);
         const int n_pairs = bytes >> 5;
         const int jt_lo = j0 + tile_index * (kTileBytes / 16), jt_hi = jt_lo + 2 * n_pairs;
-        if (jt_lo < own_hi && own_lo < jt_hi) tile_loop(t, n_pairs, std::true_type{});
-        else tile_loop(t, n_pairs, std::false_type{});
+        if (jt_lo < own_hi && own_lo < jt_hi) f32_pairs<kP, true>(t, n_pairs, xi, yi, zi, ax, ay, az, eps2);
+        else f32_pairs<kP, false>(t, n_pairs, xi, yi, zi, ax, ay, az, eps2);
     };
     stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 16, (j1 - j0) * 16, ring, bars, consume);
     pdl_release();
@@ -423,16 +368,7 @@ force_f64_kernel(const double* __restrict__ stream, int n_pad, int i0, int n_i, 
 
     auto consume = [&](const char* tile, int bytes, int) {
         const double2* __restrict__ t = reinterpret_cast<const double2*>(tile);
-        const int n_j = bytes >> 5;
-#pragma unroll 4
-        for (int j = 0; j < n_j; ++j) {
-            const double2 a = t[2 * j];      // x y
-            const double2 b = t[2 * j + 1];  // z gm
-            const double c1 = b.y * kC1OverC0;  // first-order build only (dead code otherwise): once per j
-#pragma unroll
-            for (int k = 0; k < kP; ++k)
-                pair_f64<kZeroEps>(xi[k], yi[k], zi[k], a.x, a.y, b.x, b.y, c1, eps2, ax[k], ay[k], az[k]);
-        }
+        f64_bodies<kP, kZeroEps>(t, bytes >> 5, xi, yi, zi, ax, ay, az, eps2);
     };
     stream_tiles(reinterpret_cast<const char*>(stream) + (size_t)j0 * 32, (j1 - j0) * 32, ring, bars, consume);
     pdl_release();
@@ -729,6 +665,24 @@ static int run_impl(T* sa_, T* sb_, T* vel, T* acc, int n, double dt, double sof
         if (int rc = kick_drift_impl<T>(cur, next, vel, acc, n, 0, n, dt, st)) return rc;
         T* t = cur; cur = next; next = t;
     }
+    // Mid-size systems: every step of the run in ONE cooperative launch (nb_persist.cu) -- same bits as the per-step
+    // launches below, without their fixed cost per step.  NB_NO_PERSIST=1 keeps the per-step path (tests compare).
+    if (n_steps >= 2 && n <= nb_persist_max_bodies() && ws && getenv("NB_NO_PERSIST") == nullptr &&
+        ws_bytes >= nb_workspace_bytes(n, n, sizeof(T) == 8)) {
+        int n_seg = 1;
+        nb_segment_plan(n, nullptr, &n_seg);
+        const size_t part_bytes = ((size_t)n_seg * 3 * n * sizeof(T) + 255) / 256 * 256;
+        char* region = static_cast<char*>(ws) + counter_bytes(n) + part_bytes;
+        unsigned* barrier = reinterpret_cast<unsigned*>(region);
+        int* group_counter = reinterpret_cast<int*>(region) + 8;
+        if (int rc = persist_run<T>(cur, next, vel, acc, n, dt, softening, n_steps, save_interval, sp, sv, sa,
+                                    partials<T>(ws, n), group_counter, barrier, error_word(ws, n), st))
+            return rc;
+        // the streams alternate once per step but the last: where x_n is
+        if ((n_steps - 1) % 2 == 1) { T* t = cur; cur = next; next = t; }
+        if (final_in_a) *final_in_a = (cur == sa_) ? 1 : 0;
+        return NB_OK;
+    }
     size_t snap = 1;
     for (int k = 1; k <= n_steps; ++k) {
         int flags = 0;
@@ -832,6 +786,11 @@ int nb_step_status(const void* workspace, int n, nb_stream_t s) {
     NB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)s));
     if (word == 0) return NB_OK;
     const int phase = word & 0xff, rank = word >> 8;
+    if (phase == NB_PERSIST_STALLED) {
+        nb::set_error("one-launch run: a grid barrier or a tile copy never completed; the state of this system is no "
+                      "longer valid");
+        return NB_ERR_CUDA;
+    }
     nb::set_error("sharded step: rank %d never arrived (%s); the state of this system is no longer valid", rank,
                   phase == NB_PEER_LOST_BEFORE_FORCE ? "its positions of the previous step were not published in time"
                                                      : "it did not finish the step in time");

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "nb_step_peer_f32": (_ci, [_vp, _vp, _vp, _ci, _ci, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _ci, _ci, _ci, _cd, _cd, _ci,
                                _vp, _vp, _vp, _vp, _sz, _vp]),
     "nb_step_status": (_ci, [_vp, _ci, _vp]),
+    "nb_persist_max_bodies": (_ci, []),
     "nb_run_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_run_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _vp, _sz, _ip, _vp]),
     "nb_ensemble_max_bodies": (_ci, []),
