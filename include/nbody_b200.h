@@ -159,9 +159,10 @@ int nb_step_status(const void* workspace, int n, nb_stream_t s);
  * (v_0, a_0) on entry and (v_n, a_n) on return.  Snapshot s (s = 1..n_steps/save_interval) of the
  * state after step s*save_interval goes to row block s of snap_* ((n_snap, n, 3) float64, n_snap =
  * 1 + n_steps/save_interval); row block 0 (the initial state) is written here too. */
-/* Systems of at most nb_persist_max_bodies() bodies run ALL their steps in one cooperative launch (K2p,
- * csrc/nb_persist.cu: warp-tasks on a persistent grid, one grid barrier per step) -- bit-identical to the per-step
- * launches, which environment NB_NO_PERSIST=1 selects; nb_step_status(workspace) reports a stalled launch. */
+/* Opt-in, environment NB_PERSIST=1: systems of at most nb_persist_max_bodies() bodies run ALL their steps in one
+ * cooperative launch (K2p, csrc/nb_persist.cu: warp-tasks on a persistent grid, one grid barrier per step) --
+ * bit-identical to the per-step launches and, as measured, no faster; nb_step_status(workspace) reports
+ * a stalled launch. */
 int nb_persist_max_bodies(void);
 int nb_run_f64(double* stream_a, double* stream_b, double* vel, double* acc, int n, double dt,
                double softening, int n_steps, int save_interval,

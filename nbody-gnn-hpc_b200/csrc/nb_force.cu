@@ -665,9 +665,12 @@ static int run_impl(T* sa_, T* sb_, T* vel, T* acc, int n, double dt, double sof
         if (int rc = kick_drift_impl<T>(cur, next, vel, acc, n, 0, n, dt, st)) return rc;
         T* t = cur; cur = next; next = t;
     }
-    // Mid-size systems: every step of the run in ONE cooperative launch (nb_persist.cu) -- same bits as the per-step
-    // launches below, without their fixed cost per step.  NB_NO_PERSIST=1 keeps the per-step path (tests compare).
-    if (n_steps >= 2 && n <= nb_persist_max_bodies() && ws && getenv("NB_NO_PERSIST") == nullptr &&
+    // Opt-in (environment NB_PERSIST=1): every step of the run in ONE cooperative launch (nb_persist.cu) -- the same
+    // bits as the per-step launches below.  Measured (profiles/r02_midn_persist.log): no faster than they are -- below
+    // N ~ 8k a step is the same chain of L2 round trips either way, above it the per-warp rings feed the pipes worse
+    // than K2's CTA-wide ring -- so the per-step path stays the default.
+    const char* persist_env = getenv("NB_PERSIST");
+    if (n_steps >= 2 && n <= nb_persist_max_bodies() && ws && persist_env && persist_env[0] == '1' &&
         ws_bytes >= nb_workspace_bytes(n, n, sizeof(T) == 8)) {
         int n_seg = 1;
         nb_segment_plan(n, nullptr, &n_seg);

@@ -27,11 +27,14 @@
 
 namespace nb {
 
-constexpr int kPWarpsMax = 14;             // warps per CTA: 2 CTAs x 14 warps x 72 registers fill an SM's register file
+// Two shapes.  kP = 4 bodies per lane: ONE CTA per SM, up to 16 warps, up to 128 registers -- the inner loop of K2's big
+// tile (half the shared-memory loads per interaction of kP = 2).  kP = 2 / 1: TWO CTAs per SM, up to 14 warps each,
+// 72 registers -- more, smaller tasks for the smaller systems.
 constexpr int kPStages = 2;                // ring depth per warp
 constexpr int kPTileBytes = 2048;          // 128 float32 bodies / 64 float64 bodies per tile
-constexpr int kPCtasPerSm = 2;
 constexpr int kPersistMaxBodies = 32768;
+template <int kP> struct PShape { static constexpr int warps = 14, ctas_per_sm = 2; };
+template <> struct PShape<4> { static constexpr int warps = 16, ctas_per_sm = 1; };
 
 template <typename T>
 struct PersistArgs {
@@ -257,7 +260,8 @@ __device__ __forceinline__ void persist_finish_body(const PersistArgs<T>& g, con
 }
 
 template <typename T, int kP, bool kZeroEps>
-__global__ void __launch_bounds__(kPWarpsMax * 32, kPCtasPerSm) persist_kernel(const PersistArgs<T> g) {
+__global__ void __launch_bounds__(PShape<kP>::warps * 32, PShape<kP>::ctas_per_sm)
+persist_kernel(const PersistArgs<T> g) {
     extern __shared__ __align__(128) char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     char* ring = smem + (size_t)warp * kPStages * kPTileBytes;
@@ -326,16 +330,26 @@ struct PersistPlan {
     int kP, warps, grid;
 };
 
-// kP = 2 when that still gives every CTA about a task per warp, else 1; as many warps as the busiest CTA has tasks.
+// The largest kP that still gives (nearly) every warp slot of the machine a task; as many warps per CTA as the busiest
+// CTA has tasks (capped by the shape).  NB_PERSIST_KP forces kP (experiments).
 static PersistPlan persist_plan(int n, int n_seg, int sms) {
     PersistPlan p;
-    const int ctas = sms * kPCtasPerSm;
-    const long tasks2 = (long)ceil_div(n, 64) * n_seg;
-    p.kP = tasks2 >= 12L * ctas ? 2 : 1;
+    p.kP = 1;
+    for (int kp : {4, 2}) {
+        const int ctas = sms * (kp == 4 ? PShape<4>::ctas_per_sm : PShape<2>::ctas_per_sm);
+        const long tasks = (long)ceil_div(n, 32 * kp) * n_seg;
+        if (tasks >= 12L * ctas) { p.kP = kp; break; }
+    }
+    if (const char* e = getenv("NB_PERSIST_KP")) {
+        const int kp = atoi(e);
+        if (kp == 1 || kp == 2 || kp == 4) p.kP = kp;
+    }
+    const int ctas = sms * (p.kP == 4 ? PShape<4>::ctas_per_sm : PShape<2>::ctas_per_sm);
+    const int wmax = p.kP == 4 ? PShape<4>::warps : PShape<2>::warps;
     const long tasks = (long)ceil_div(n, 32 * p.kP) * n_seg;
     p.grid = (int)(tasks < ctas ? tasks : ctas);
     const int per_cta = (int)((tasks + p.grid - 1) / p.grid);
-    p.warps = per_cta < kPWarpsMax ? per_cta : kPWarpsMax;
+    p.warps = per_cta < wmax ? per_cta : wmax;
     if (p.warps < 1) p.warps = 1;
     return p;
 }
@@ -361,10 +375,11 @@ int persist_run(T* stream_a, T* stream_b, T* vel, T* acc, int n, double dt, doub
     g.timeout_ns = 5000000000ull;
     const bool zero = !(g.eps2 > T(0));
     void (*kern)(const PersistArgs<T>);
-    if (plan.kP == 2) kern = zero ? persist_kernel<T, 2, true> : persist_kernel<T, 2, false>;
+    if (plan.kP == 4) kern = zero ? persist_kernel<T, 4, true> : persist_kernel<T, 4, false>;
+    else if (plan.kP == 2) kern = zero ? persist_kernel<T, 2, true> : persist_kernel<T, 2, false>;
     else kern = zero ? persist_kernel<T, 1, true> : persist_kernel<T, 1, false>;
     const size_t smem = (size_t)plan.warps * kPStages * (kPTileBytes + sizeof(uint64_t));
-    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPWarpsMax * kPStages * (kPTileBytes + 8))));
+    NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * kPStages * (kPTileBytes + 8))));
     int per_sm = 0;
     NB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan.warps * 32, smem));
     NB_REQUIRE((long)per_sm * sms >= plan.grid, "persistent step kernel: %d CTAs cannot be resident at once (%d per SM)",

@@ -490,19 +490,19 @@ def test_interval_schedule_with_another_tenant_on_the_gpu(engine):
                                                  (4096, "float64", 3, 1), (16384, "float32", 6, 6), (9000, "float64", 2, 1),
                                                  (20000, "float32", 3, 1), (32768, "float32", 2, 2)])
 def test_one_launch_run_bitwise_equals_per_step_launches(engine, monkeypatch, n, dtype, steps, every):
-    """K2p (csrc/nb_persist.cu: all steps of a run in ONE cooperative launch, warp-tasks on a persistent grid, one
-    grid barrier per step) against K2 (one launch per step, NB_NO_PERSIST=1): the final state and every snapshot row
-    must be the same BITS -- same segment plan, same inner loops, same epilogue arithmetic."""
+    """K2p (csrc/nb_persist.cu, opt-in with NB_PERSIST=1: all steps of a run in ONE cooperative launch, warp-tasks on a
+    persistent grid, one grid barrier per step) against K2 (one launch per step, the default): the final state and
+    every snapshot row must be the same BITS -- same segment plan, same inner loops, same epilogue arithmetic."""
     import torch
     from hpc import ics
     from hpc.sharded import ShardedSystem
     x, v, m = ics.plummer_ic(n, seed=13)
     res = {}
     for mode in ("persist", "per_step"):
-        if mode == "per_step":
-            monkeypatch.setenv("NB_NO_PERSIST", "1")
+        if mode == "persist":
+            monkeypatch.setenv("NB_PERSIST", "1")
         else:
-            monkeypatch.delenv("NB_NO_PERSIST", raising=False)
+            monkeypatch.delenv("NB_PERSIST", raising=False)
         s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=np.dtype(dtype), device=engine.device)
         n_snap = 1 + steps // every
         snaps = tuple(torch.zeros((n_snap, n, 3), dtype=torch.float64, device=engine.device) for _ in range(3))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Mid-size single systems, leapfrog step time: the one-launch kernel (K2p, nb_persist.cu) against one launch per step
-(K2, NB_NO_PERSIST=1); ms per step, interactions/s, fraction of the 20-flop pipe peak."""
+(K2, the default; K2p is opt-in with NB_PERSIST=1); ms per step, interactions/s, fraction of the 20-flop pipe peak."""
 import json
 import os
 import sys
@@ -22,10 +22,10 @@ for dtype, lanes in ((np.float32, 128), (np.float64, 64)):
         x, v, m = ics.plummer_ic(n, seed=7)
         row = {"n": n, "dtype": np.dtype(dtype).name}
         for mode in ("one_launch", "per_step"):
-            if mode == "per_step":
-                os.environ["NB_NO_PERSIST"] = "1"
+            if mode == "one_launch":
+                os.environ["NB_PERSIST"] = "1"
             else:
-                os.environ.pop("NB_NO_PERSIST", None)
+                os.environ.pop("NB_PERSIST", None)
             s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=dtype, device=0)
             steps = max(10, min(400, int(2e12 / (n * float(n)))))
             s.advance(steps)
