@@ -485,6 +485,7 @@ def bench_ensemble(args, world, rank, local):
             extra["snapshot_energies_300x401x200"] = snapshot_energy_extras(eng, outs[0][0], outs[0][1], m32)
             extra["e2e_device_resident"] = device_resident_extras(eng, x0, v0, m32, dtype, inter_step)
             extra["simulator_api_N200_400_steps"] = simulator_api_extras(local, numba_api_ms)
+            extra["e2e_positions_velocities_only"] = e2e_fields_extras(x0, v0, m32, dtype, local, inter_step)
         del outs
         torch.cuda.empty_cache()
         extra.update(sharded_extras(eng, world, rank, local))           # every rank takes part
@@ -589,6 +590,29 @@ def device_resident_extras(eng, x0, v0, m32, dtype, inter_step) -> dict:
     return {"value": round(inter_step / secs / 1e9, 2), "unit": UNIT, "ms_per_step": round(secs * 1e3, 3),
             "h2d_bytes_per_step": int(x0.nbytes + v0.nbytes + m32.nbytes), "d2h_bytes_per_step": int(3 * x0.nbytes + 4),
             "api": "simulate_ensemble(host ICs, outputs='device') -> sliding_windows_device(L=10): float32 samples in HBM"}
+
+
+def e2e_fields_extras(x0, v0, m32, dtype, local, inter_step) -> dict:
+    """The host-array API with fields=("positions", "velocities"): what create_training_dataset (reference
+    checkpoint.py:362-384) actually consumes.  The accelerations stay in HBM (fetched if the caller reads them)."""
+    from hpc.ensemble import simulate_ensemble
+
+    def once():
+        out = simulate_ensemble(x0, v0, m32, dt=1e-3, softening=1e-9, n_steps=ENS_STEPS, save_interval=1, dtype=dtype,
+                                device=local, fields=("positions", "velocities"))
+        return out["positions"][0, -1, 0, 0]
+
+    once()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    secs = (time.perf_counter() - t0) / reps
+    B, n_snap, N = ENS_B, ENS_STEPS + 1, ENS_N
+    return {"value": round(inter_step / secs / 1e9, 2), "unit": UNIT, "ms_per_step": round(secs * 1e3, 3),
+            "h2d_bytes_per_step": int(x0.nbytes + v0.nbytes + m32.nbytes),
+            "d2h_bytes_per_step": int(2 * B * n_snap * N * 24 + 3 * B * N * 24),
+            "api": "simulate_ensemble(host ndarrays, fields=('positions','velocities')) -> host ndarrays"}
 
 
 def simulator_api_extras(local: int, numba_api_ms) -> dict:

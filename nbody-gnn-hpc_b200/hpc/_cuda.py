@@ -139,6 +139,58 @@ def _current_device(torch) -> int:
     return int(get()) if get is not None else int(torch.cuda.current_device())
 
 
+class DeferredDict(dict):
+    """A result dict some of whose entries are still on the device: a deferred entry is fetched (one device -> host
+    copy) the first time it is read, and is an ordinary entry from then on."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._deferred = {}
+
+    def defer(self, key, fetch) -> None:
+        self._deferred[key] = fetch
+
+    def deferred(self):
+        return tuple(self._deferred)
+
+    def _fetch_all(self) -> None:
+        for key in list(self._deferred):
+            self[key]
+
+    def __getitem__(self, key):
+        fetch = self._deferred.pop(key, None)
+        if fetch is not None:
+            super().__setitem__(key, fetch())
+        return super().__getitem__(key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __contains__(self, key):
+        return key in self._deferred or super().__contains__(key)
+
+    def __iter__(self):
+        yield from super().__iter__()
+        yield from self._deferred
+
+    def __len__(self):
+        return super().__len__() + len(self._deferred)
+
+    def keys(self):
+        return list(iter(self))
+
+    def values(self):
+        self._fetch_all()
+        return super().values()
+
+    def items(self):
+        self._fetch_all()
+        return super().items()
+
+
+SNAPSHOT_FIELDS = ("positions", "velocities", "accelerations")
+
+
 class Engine:
     """One CUDA device's view of the library.  Mirrors the reference operations one to one."""
 
@@ -481,12 +533,20 @@ class Engine:
         self.launches += 1
 
     def ensemble(self, x0, v0, masses, dt: float, softening: float, n_steps: int, save_interval: int = 1,
-                 dtype=np.float64, a0=None, snapshots: bool = True, outputs: str = "host") -> dict:
+                 dtype=np.float64, a0=None, snapshots: bool = True, outputs: str = "host", fields=None) -> dict:
         """B independent systems (reference generate_data.py:32-58,142-149): host arrays in and out.
 
         x0, v0: (B,N,3); masses: (N,) shared or (B,N).  a0 None -> evaluated from x0 (what the
         scripts do after assigning the shared masses, generate_data.py:47).
+        fields: which snapshot stacks cross PCIe with the run (default: all three).  A stack that is left out stays in
+        HBM and is fetched when the result's entry is first read (DeferredDict) -- the accelerations are a third of
+        the 1.74 GB of a 300 x 200 x 400 run and create_training_dataset (reference checkpoint.py:362-384) never
+        reads them.
         """
+        eager = SNAPSHOT_FIELDS if fields is None else tuple(fields)
+        for f in eager:
+            if f not in SNAPSHOT_FIELDS:
+                raise ValueError(f"fields must be a subset of {SNAPSHOT_FIELDS}, got {f!r}")
         torch = _torch()
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         v0 = np.ascontiguousarray(v0, dtype=np.float64)
@@ -536,7 +596,8 @@ class Engine:
                                      n_snap_total=n_snap, snap_offset=0)
                 return {"positions": ox, "velocities": ov, "accelerations": oa, "final_positions": self.to_host(x),
                         "final_velocities": self.to_host(v), "final_accelerations": self.to_host(a)}
-            host = [torch.empty((B, n_snap, N, 3), dtype=torch.float64, pin_memory=True) for _ in range(3)]
+            host = [torch.empty((B, n_snap, N, 3), dtype=torch.float64, pin_memory=True) if name in eager else None
+                    for name in SNAPSHOT_FIELDS]
             # (Letting the kernel store its rows straight into the pinned host arrays through UVA was measured
             # too: 35.4 ms per 300x200x400 ensemble against 34.6 ms for the staged, chunked copy below.)
             ox = torch.empty((B, n_snap, N, 3), dtype=torch.float64, device=self.device)
@@ -572,15 +633,21 @@ class Engine:
                     copier.wait_event(done)
                     pitch = n_snap * row_bytes
                     for dev_t, host_t in zip((ox, ov, oa), host):
+                        if host_t is None:
+                            continue
                         self._check(self.lib.nb_copy_rows_d2h_async(
                             ctypes.c_void_p(host_t.data_ptr() + row0 * row_bytes), pitch,
                             ctypes.c_void_p(dev_t.data_ptr() + row0 * row_bytes), pitch, rows * row_bytes, B,
                             ctypes.c_void_p(copier.cuda_stream)))
                 row0 += rows
-            res = {"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
-                   "final_accelerations": self.to_host(a)}
+            res = DeferredDict({"final_positions": self.to_host(x), "final_velocities": self.to_host(v),
+                                "final_accelerations": self.to_host(a)})
             copier.synchronize()
-            res.update(positions=host[0].numpy(), velocities=host[1].numpy(), accelerations=host[2].numpy())
+            for name, dev_t, host_t in zip(SNAPSHOT_FIELDS, (ox, ov, oa), host):
+                if host_t is not None:
+                    res[name] = host_t.numpy()
+                else:
+                    res.defer(name, lambda t=dev_t: self.to_host(t))     # keeps the device stack alive until read
             return res
 
     def _copy_stream(self):

@@ -18,7 +18,7 @@ __all__ = ["simulate_ensemble", "generate_simulations", "generate_single_simulat
 
 def simulate_ensemble(positions, velocities, masses, dt: float = 1e-3, softening: float = nbody.SOFTENING,
                       n_steps: int = 400, save_interval: int = 1, *, dtype=None, accelerations=None,
-                      snapshots: bool = True, device=None, outputs: str = "host") -> dict:
+                      snapshots: bool = True, device=None, outputs: str = "host", fields=None) -> dict:
     """Advance B independent systems of N bodies by n_steps kick-drift-kick steps.
 
     positions, velocities: (B,N,3); masses: (N,) shared by all systems or (B,N).
@@ -27,11 +27,15 @@ def simulate_ensemble(positions, velocities, masses, dt: float = 1e-3, softening
     ``np.stack([s[key] for s in sim.run(...)])`` yields -- plus 'times' and the final state.
     outputs="device" leaves the stacks in HBM as torch tensors (72*N bytes per system-step never cross PCIe):
     the input of the window kernel (``hpc.checkpoint.sliding_windows_device``) and of anything else on the GPU.
+    fields=("positions", "velocities") ships only those stacks with the run; the others stay in HBM and are copied
+    when the result's entry is first read (the run is PCIe-bound: a stack nobody reads is a third of its time).
     """
     if outputs not in ("host", "device"):
         raise ValueError("outputs must be 'host' or 'device'")
     eng = nbody._cuda.get_engine(device)
     kw = {"outputs": outputs} if outputs != "host" else {}
+    if fields is not None:
+        kw["fields"] = fields
     out = eng.ensemble(positions, velocities, masses, float(dt), float(softening), int(n_steps), int(save_interval),
                        dtype=nbody._engine_dtype(dtype), a0=accelerations, snapshots=snapshots, **kw)
     t, times = 0.0, [0.0]

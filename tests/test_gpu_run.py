@@ -513,3 +513,19 @@ def test_one_launch_run_bitwise_equals_per_step_launches(engine, monkeypatch, n,
     for a, b in zip(res["persist"], res["per_step"]):
         assert torch.equal(a, b)
     assert torch.isfinite(res["persist"][0]).all() and (res["persist"][3][1:] != 0).any()
+
+
+def test_ensemble_deferred_fields(engine):
+    """fields=(...) ships only the named snapshot stacks with the run; the others stay in HBM until first read."""
+    from hpc import ics
+    from hpc.ensemble import simulate_ensemble
+    x0, v0, m32 = ics.datagen_ensemble_ic(5, 200, seed=3)
+    full = simulate_ensemble(x0, v0, m32, dt=1e-3, n_steps=9, save_interval=3)
+    part = simulate_ensemble(x0, v0, m32, dt=1e-3, n_steps=9, save_interval=3, fields=("positions", "velocities"))
+    assert part.deferred() == ("accelerations",) and "accelerations" in part and len(part) == len(full)
+    assert np.array_equal(part["positions"], full["positions"]) and np.array_equal(part["velocities"], full["velocities"])
+    acc = part["accelerations"]                                  # first read: the device -> host copy happens now
+    assert part.deferred() == () and np.array_equal(acc, full["accelerations"]) and part["accelerations"] is acc
+    assert np.array_equal(part["times"], full["times"])
+    with pytest.raises(ValueError):
+        simulate_ensemble(x0, v0, m32, n_steps=2, fields=("momenta",))
