@@ -148,7 +148,7 @@ int nb_energy_f64(const double* pos, const double* vel, const void* masses, int 
 // ------------------------------------------------------------------------------------------------------------------
 namespace nb {
 
-constexpr int kSnapEnergyMaxBodies = 4096;  // 4 doubles per body in shared memory (128 KB)
+constexpr int kSnapEnergyMaxBodies = 4096;  // 4 doubles + 1 float per body in shared memory (144 KB)
 
 // kF32Product: the masses are float32 and the reference forms m_i * m_j in float32 (np.outer of a float32 array,
 // metrics.py:82): the product is rounded the same way here, so the energies agree to float64 rounding, not 1e-8.
@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(256)
 snapshot_energy_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
                        const void* __restrict__ masses, int masses_are_f32, int mass_stride, int S, int N, double G,
                        double eps2, double* __restrict__ out) {
-    extern __shared__ __align__(16) double4 body[];  // x, y, z, m
+    extern __shared__ __align__(16) double4 body[];  // x, y, z, m; behind them (kF32Product) the masses as float
     __shared__ double red[5][8];
+    float* mf = reinterpret_cast<float*>(body + N);
     const int snap = blockIdx.x;                  // b * S + s
     const int b = snap / S;
     const double* x = pos + (size_t)snap * N * 3;
@@ -168,32 +169,42 @@ snapshot_energy_kernel(const double* __restrict__ pos, const double* __restrict_
         return masses_are_f32 ? (double)static_cast<const float*>(masses)[mi] : static_cast<const double*>(masses)[mi];
     };
     const bool potential = pos != nullptr;  // momentum / kinetic energy only (compute_momentum_error) when null
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-        body[i] = potential ? make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], mass(i)) : make_double4(0., 0., 0., mass(i));
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double m = mass(i);
+        body[i] = potential ? make_double4(x[3 * i], x[3 * i + 1], x[3 * i + 2], m) : make_double4(0., 0., 0., m);
+        if (kF32Product) mf[i] = (float)m;
+    }
     __syncthreads();
     double k = 0.0, u = 0.0, px = 0.0, py = 0.0, pz = 0.0;
     const int half = N / 2;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         const double4 me = body[i];
+        const float mfi = kF32Product ? mf[i] : 0.f;
         const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
         k += 0.5 * me.w * (vx * vx + vy * vy + vz * vz);
         px += me.w * vx;
         py += me.w * vy;
         pz += me.w * vz;
-        // partners i+1 .. i+half (mod N); for even N the last one (distance N/2) is shared with the partner: the
-        // lower index takes it
+        // partners i+1 .. i+cnt (mod N); for even N the pair at distance N/2 is shared with the partner and the lower
+        // index takes it.  Two straight runs -- up to the end of the array, then from its start -- so the loops have
+        // plain increments and unroll.
         const int cnt = !potential ? 0 : (N % 2 == 0 && i >= half) ? half - 1 : half;
         double phi = 0.0;
-        int j = i + 1 < N ? i + 1 : 0;
+        auto run = [&](int j0, int j1) {
 #pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            const double4 p = body[j];
-            const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
-            const double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
-            const double mm = kF32Product ? (double)((float)me.w * (float)p.w) : p.w;
-            phi += r2 > 0.0 ? mm * rsqrt_f64(r2) : 0.0;
-            j = j + 1 < N ? j + 1 : 0;
-        }
+            for (int j = j0; j < j1; ++j) {
+                const double4 p = body[j];
+                const double dx = p.x - me.x, dy = p.y - me.y, dz = p.z - me.z;
+                const double r2 = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
+                // float32 masses: the product is formed in float32 like the reference's np.outer (one FMUL, one
+                // conversion: conversions share the MUFU pipe)
+                const double mm = kF32Product ? (double)__fmul_rn(mfi, mf[j]) : p.w;
+                phi += r2 > 0.0 ? mm * rsqrt_f64(r2) : 0.0;
+            }
+        };
+        const int first_end = min(N, i + 1 + cnt);
+        run(i + 1, first_end);
+        run(0, cnt - (first_end - (i + 1)));
         u -= kF32Product ? G * phi : G * me.w * phi;
     }
     double vals[5] = {k, u, px, py, pz};
@@ -226,7 +237,7 @@ int nb_snapshot_energy_f64(const double* pos, const double* vel, const void* mas
                nb::kSnapEnergyMaxBodies, B, S, N);
     NB_REQUIRE(mass_stride == 0 || mass_stride == N, "mass_stride must be 0 (shared) or N");
     NB_REQUIRE((long long)B * S <= 0x7fffffffLL, "too many snapshots");
-    const size_t smem = (size_t)N * sizeof(double4);
+    const size_t smem = (size_t)N * (sizeof(double4) + sizeof(float));
     auto kern = masses_are_f32 ? nb::snapshot_energy_kernel<true> : nb::snapshot_energy_kernel<false>;
     NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int threads = nb::round_up(N < 256 ? N : 256, 32);
