@@ -66,6 +66,22 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// Bounds / protocol checks of our own (compute-sanitizer is closed on the pool): compiled in by -DNB_DEBUG_CHECKS
+// (build.py --out lib/variants/libnb_debug.so -D NB_DEBUG_CHECKS), the GPU tests then run against that library
+// (NBODY_B200_LIB).  A failed check prints where and traps, which the host sees as a launch failure.
+#ifdef NB_DEBUG_CHECKS
+#define NB_CHECK(cond)                                                                             \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            printf("NB_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)threadIdx.x);                                             \
+            __trap();                                                                              \
+        }                                                                                          \
+    } while (0)
+#else
+#define NB_CHECK(cond) ((void)0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -202,6 +202,7 @@ snapshot_energy_kernel(const double* __restrict__ pos, const double* __restrict_
                 phi += r2 > 0.0 ? mm * rsqrt_f64(r2) : 0.0;
             }
         };
+        NB_CHECK(cnt >= 0 && cnt <= half && i < N);
         const int first_end = min(N, i + 1 + cnt);
         run(i + 1, first_end);
         run(0, cnt - (first_end - (i + 1)));

@@ -319,6 +319,7 @@ __device__ __forceinline__ void force_phase(const EnsembleArgs& g, const SystemS
         pair_any<kZeroEps>(me0.x, me0.y, me0.z, pj.x, pj.y, pj.z, pj.w, c1, eps2, ax0, ay0, az0);
         pair_any<kZeroEps>(me1.x, me1.y, me1.z, pj.x, pj.y, pj.z, pj.w, c1, eps2, ax1, ay1, az1);
     }
+    NB_CHECK(q >= 0 && q < parts && jb >= 0 && jb <= je && je <= N && i0 < N && (!has1 || i1 < N));
     T* pa = s.part + (size_t)q * n3;
     pa[3 * i0 + 0] = ax0; pa[3 * i0 + 1] = ay0; pa[3 * i0 + 2] = az0;
     if (has1) { pa[3 * i1 + 0] = ax1; pa[3 * i1 + 1] = ay1; pa[3 * i1 + 2] = az1; }
@@ -346,7 +347,9 @@ __device__ __forceinline__ void integrate_phase(const EnsembleArgs& g, const Pie
         }
     }
     const size_t orow = srow >= 0 ? ((size_t)p.b * g.n_snap_total + (size_t)srow) * n3 : 0;
+    NB_CHECK(srow < (long)g.n_snap_total && p.b >= 0 && p.b < g.B && k >= p.k0 && k <= p.k1 && p.k1 <= g.n_steps);
     for_each_owned(own, n3, [&](int idx, int poff) {
+        NB_CHECK(idx >= 0 && idx < n3 && poff >= 0 && poff < 4 * N);
         T a = s.acc[idx];
         if (do_force) {
             a = s.part[idx];
@@ -634,6 +637,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) cluster_ensemble_kernel(const 
                 if (do_open) {
                     v = mul_add_unfused(half_dt, a, v);  // opening kick, nbody.py:205
                     x = mul_add_unfused(dt, v, x);       // drift, nbody.py:208
+                    NB_CHECK(i_lo + li < N && c < 3 && (cur == 0 || cur == 1));
                     const uint32_t off = (uint32_t)(((size_t)(cur ^ 1) * 4 * N + 4 * (i_lo + li) + c) * sizeof(T));
 #pragma unroll
                     for (int t = 0; t < kClusterCtas; ++t)

@@ -52,6 +52,8 @@ __device__ __forceinline__ void stream_tiles(const char* __restrict__ src, int t
         const int slot = t % kStages;
         mbar_wait(&bars[slot], (t / kStages) & 1);
         const int bytes = min(kTileBytes, total_bytes - t * kTileBytes);
+        NB_CHECK(bytes > 0 && bytes % 32 == 0 && slot >= 0 && slot < kStages);
+        NB_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0);
         consume(ring + slot * kTileBytes, bytes, t);
         __syncthreads();  // every thread is done with this slot before it is refilled
         const int nt = t + kStages;
@@ -178,6 +180,7 @@ struct Epilogue {
 template <typename T>
 __device__ __forceinline__ void finish_body(const Epilogue<T>& e, const T* partial, int i0, int n_i, int li,
                                             T x_out[3]) {
+    NB_CHECK(li >= 0 && li < n_i && e.n_seg >= 1 && e.n_seg <= 64);
     T a[3] = {T(0), T(0), T(0)};
     for (int s = 0; s < e.n_seg; ++s) {
         const T* p = partial + (size_t)s * 3 * n_i;
@@ -231,6 +234,7 @@ __device__ __forceinline__ void peer_records(const Epilogue<float>& e, int gi, b
     const float x1 = __shfl_down_sync(0xffffffffu, x[0], 1);
     const float y1 = __shfl_down_sync(0xffffffffu, x[1], 1);
     const float z1 = __shfl_down_sync(0xffffffffu, x[2], 1);
+    NB_CHECK(!valid || gi >= 0);
     if (valid && !(gi & 1) && (e.flags & NB_STEP_CONTINUE)) {
         const float4 b = reinterpret_cast<const float4*>(e.cur)[(size_t)gi + 1];  // z0 z1 gm0 gm1 of this pair
         store_record_to_peers<float4>(e.peers, (size_t)gi, make_float4(x[0], x1, x[1], y1),
@@ -249,6 +253,10 @@ __device__ __forceinline__ void tile_epilogue(const Epilogue<T>& e, const T* par
     if (threadIdx.x == 0) s_last = atomicAdd(e.tile_counter + blockIdx.x, 1) == (int)gridDim.y - 1;
     __syncthreads();
     if (!s_last) return;
+#ifdef NB_DEBUG_CHECKS
+    NB_CHECK(*reinterpret_cast<volatile int*>(e.tile_counter + blockIdx.x) == (int)gridDim.y);  // every segment arrived once
+    __syncthreads();
+#endif
     if (threadIdx.x == 0) e.tile_counter[blockIdx.x] = 0;  // ready for the next launch
     __threadfence();
 #pragma unroll
@@ -302,6 +310,7 @@ force_f32_kernel(const float* __restrict__ stream, int n_pad, int i0, int n_i, i
     const int j0 = seg * seg_len;
     const int j1 = min(j0 + seg_len, n_pad);
     const int li0 = blockIdx.x * (kBlock * kP) + threadIdx.x;
+    NB_CHECK(j0 < j1 && (j0 % kChunkBodies) == 0 && (j1 % kChunkBodies) == 0 && i0 >= 0 && i0 + n_i <= n_pad);
 
     float xi[kP], yi[kP], zi[kP];
     float2 ax[kP], ay[kP], az[kP];

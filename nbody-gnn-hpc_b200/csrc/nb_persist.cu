@@ -292,6 +292,7 @@ persist_kernel(const PersistArgs<T> g) {
         for (int t = t_lo + warp; t < t_hi && ok; t += n_warps) {
             const int grp = t / g.n_seg, seg = t - grp * g.n_seg;
             const int j0 = seg * g.seg_len, j1 = min(j0 + g.seg_len, g.n_pad);
+            NB_CHECK(grp >= 0 && grp < g.n_groups && seg >= 0 && seg < g.n_seg && j0 < j1);
             ok = WarpTask<T, kP, kZeroEps>::run(cur, g.n, grp, j0, j1, g.eps2, g.partial + (size_t)seg * 3 * g.n, ring,
                                                 bars, tiles_done, lane);
             if (!ok) break;

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) window_stream_kernel(const WindowArgs g) 
             for (int s = s_next + threadIdx.x; s < s_done; s += blockDim.x) {
                 const size_t sample = (size_t)b * g.S + s;
                 const int first = (s * g.stride - i_a) % g.ring;                   // ring slot of the window's first state
+                NB_CHECK(first >= 0 && first < g.ring && g.L < g.ring);
                 const int run1 = min(g.L, g.ring - first);                          // states before the ring wraps
                 float* in = g.inputs + sample * (size_t)g.L * n6;
                 bulk_store(in, ring + (size_t)first * n6, (uint32_t)run1 * state_bytes);
