@@ -97,3 +97,32 @@ def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
     monkeypatch.setenv("NBODY_B200_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(_cuda.EngineUnavailable, match="no CPU fallback"):
         _cuda.load_library()
+
+
+def test_bad_arguments_of_the_round2_entry_points():
+    """nb_snapshot_energy_f64, nb_step_peer_*, nb_step_status, nb_probe_occupy: argument errors are return codes with a
+    message (checked before any CUDA call, so this runs without a GPU)."""
+    import ctypes
+    from hpc import _cuda
+    lib = _cuda.load_library()
+    buf = ctypes.create_string_buffer(4096)
+    assert lib.nb_snapshot_energy_max_bodies() >= 1024 and lib.nb_persist_max_bodies() >= 16384
+    rc = lib.nb_snapshot_energy_f64(buf, None, buf, 0, 0, 1, 1, 4, 6.6743e-11, 1e-9, buf, None)      # vel null
+    assert rc == 1 and b"null" in lib.nb_last_error()
+    rc = lib.nb_snapshot_energy_f64(buf, buf, buf, 0, 0, 1, 1, 10 ** 6, 6.6743e-11, 1e-9, buf, None)  # N too large
+    assert rc == 1 and b"N <=" in lib.nb_last_error()
+    rc = lib.nb_snapshot_energy_f64(buf, buf, buf, 0, 3, 2, 2, 4, 6.6743e-11, 1e-9, buf, None)         # stride not 0 / N
+    assert rc == 1 and b"mass_stride" in lib.nb_last_error()
+    ptrs = (ctypes.c_void_p * 2)(ctypes.addressof(buf), ctypes.addressof(buf))
+    ws_bytes = lib.nb_workspace_bytes(64, 32, 1)
+    rc = lib.nb_step_peer_f64(buf, ptrs, ptrs, 2, 5, 0, 1, buf, buf, 64, 0, 32, 1e-3, 1e-9, 0, None, None, None, buf,
+                              ws_bytes, None)                                                          # my_rank >= n_ranks
+    assert rc == 1 and b"my_rank" in lib.nb_last_error()
+    rc = lib.nb_step_peer_f64(buf, ptrs, ptrs, 2, 1, 0, 1, buf, buf, 64, 16, 32, 1e-3, 1e-9, 0, None, None, None, buf,
+                              ws_bytes, None)                                                          # slab start not a chunk
+    assert rc == 1 and b"multiple of 32" in lib.nb_last_error()
+    rc = lib.nb_step_peer_f64(buf, ptrs, ptrs, 2, 1, 0, 1, buf, buf, 64, 32, 32, 1e-3, 1e-9, 0, None, None, None, buf,
+                              16, None)                                                                # workspace too small
+    assert rc == 1 and b"workspace too small" in lib.nb_last_error()
+    assert lib.nb_step_status(None, 64, None) == 1 and lib.nb_probe_occupy(0, 0, 1.0, None) == 1
+    assert lib.nb_workspace_bytes(4096, 4096, 0) > lib.nb_workspace_bytes(4096, 2048, 0)   # whole-system workspaces carry K2p's words
