@@ -145,10 +145,14 @@ __host__ __device__ inline size_t lane_smem_bytes(int N, int parts) {
     return (b + 15) / 16 * 16;
 }
 
-// Thread shape for N bodies: two bodies per thread, as many j-parts as fit in 512 threads (at most 8).
+// Thread shape for N bodies: two bodies per thread, as many j-parts as fit in kForceThreadsMax threads (at most 8).
+#ifndef NB_K3_FORCE_THREADS
+#define NB_K3_FORCE_THREADS 512
+#endif
+constexpr int kForceThreadsMax = NB_K3_FORCE_THREADS;  // rows x parts never exceeds it (shape_parts)
 __host__ __device__ constexpr int shape_rows(int N) { return (N + 1) / 2; }
 __host__ __device__ constexpr int shape_parts(int N) {
-    int p = 512 / shape_rows(N);
+    int p = kForceThreadsMax / shape_rows(N);
     p = p < 1 ? 1 : p;
     p = p > 8 ? 8 : p;
     return p > N ? N : p;
@@ -376,7 +380,7 @@ __device__ __forceinline__ void integrate_phase(const EnsembleArgs& g, const Pie
 }
 
 constexpr int kMaxLanes = 2;
-constexpr int kForceThreadsMax = 512;                  // rows x parts never exceeds it (shape_parts)
+static_assert(kForceThreadsMax % 32 == 0 && kForceThreadsMax + 128 <= 1024, "force + integrator warps must fit one CTA");
 constexpr int kIntegratorThreads = 128;                // the integrator warps of the two-lane mode
 constexpr int kEnsembleThreadsMax = kForceThreadsMax + kIntegratorThreads;
 

@@ -2,6 +2,7 @@
 """Digest an .ncu-rep (ncu --set full) into profiles/<tag>_ncu_full_summary.csv and profiles/summary.json.
 
     python tools/ncu_digest.py gpurun_out/prof_r1c.ncu-rep r01c "tools/profile_target.py ens400 f32 f64"
+    python tools/ncu_digest.py gpurun_out/prof_r02_raw.csv r02 "..."        # a raw-page CSV exported on the GPU box
 
 Runs here (no GPU needed): `ncu -i <rep> --page raw --csv` is parsed, one row per captured launch with the columns
 the design document quotes, and a per-kernel digest (the last captured launch of each kernel) is written to
@@ -35,7 +36,11 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us"
 
 def main():
     rep, tag, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    if rep.endswith(".csv"):   # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): reports can exceed
+        raw = Path(rep).read_text()                                          # what gpurun copies back
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    raw = raw[raw.index('"ID"'):] if '"ID"' in raw else raw
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], dict(zip(rows[0], rows[1]))
     out = io.StringIO()
