@@ -76,7 +76,6 @@ if "snap" in which:
     torch.cuda.synchronize()
 if "peer" in which:
     # the fused force + leapfrog + peer-store step kernel, one rank that is its own peer, N = 65,536 float32
-    from hpc.sharded import slab_bounds  # noqa: F401
     n = 65536
     x, v, m = ics.plummer_ic(n, seed=7)
     pos_d = eng.to_device(x)
