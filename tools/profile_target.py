@@ -94,4 +94,18 @@ if "peer" in which:
         cur, nxt = nxt, cur
     torch.cuda.synchronize()
     eng.step_status(ws, n)
+if "persist" in which:
+    # K2p (opt-in): ten leapfrog steps of N = 16,384 in one cooperative launch, both precisions
+    import os
+    from hpc.sharded import ShardedSystem
+    os.environ["NB_PERSIST"] = "1"
+    n = 16384
+    x, v, m = ics.plummer_ic(n, seed=7)
+    for dtype in (np.float32, np.float64):
+        s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=dtype, device=0)
+        for _ in range(2):
+            s.advance(10)
+        torch.cuda.synchronize()
+        eng.step_status(s.ws, n)
+    os.environ.pop("NB_PERSIST", None)
 print("ok")
