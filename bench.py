@@ -218,6 +218,62 @@ def _numba_api_timings(_=None):
     return best_run * 1e3, best_loop * 1e3
 
 
+def _numba_force_timings(path: str, sizes, q) -> None:
+    """Child process: the reference's compute_accelerations_direct (src/hpc/nbody.py:22-66, Numba parallel=True) with
+    ALL host threads, one warm-up call per size (JIT excluded), mean of 5 -- SURVEY 8(d) item (1)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_nbody", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    import numba
+    out = {"threads": int(numba.get_num_threads()), "threading_layer": None, "G_interactions_per_s": {}}
+    rng = np.random.RandomState(7)
+    for n in sizes:
+        x = rng.standard_normal((n, 3))
+        m = np.full(n, 1.0 / (6.67430e-11 * n))
+        ref.compute_accelerations_direct(x, m, 0.01)
+        reps = 5 if n <= 4096 else 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref.compute_accelerations_direct(x, m, 0.01)
+        dt = (time.perf_counter() - t0) / reps
+        out["G_interactions_per_s"][str(n)] = round(n * (n - 1.0) / dt / 1e9, 3)
+    try:
+        out["threading_layer"] = numba.threading_layer()
+    except Exception:
+        pass
+    q.put(out)
+
+
+def numba_force_eval_extras(sizes=(1024, 4096, 16384)):
+    """The reference's force evaluation on all host cores (a fresh process: the pool's workers are single-threaded)."""
+    import multiprocessing as mp
+    if not REF_FILE.exists():
+        return None
+    cores = os.cpu_count() or 1
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "NUMBA_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    try:
+        for k in saved:
+            os.environ[k] = str(cores)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_numba_force_timings, args=(str(REF_FILE), list(sizes), q))
+        p.start()
+        out = q.get(timeout=240)
+        p.join(timeout=30)
+    except Exception as e:                      # noqa: BLE001
+        return {"unavailable": repr(e)[:200]}
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    out["cores"] = cores
+    out["what"] = "reference compute_accelerations_direct (Numba parallel=True), Plummer-like ICs, eps = 0.01, JIT excluded"
+    return out
+
+
 class NumbaEnsemble:
     """The reference's data-generation path on the host cores: mp.Pool(cores) of single-threaded Numba workers
     (scripts/generate_data.py:16-19,143-147) running the UNMODIFIED src/hpc/nbody.py from baseline/_ref."""
@@ -486,6 +542,9 @@ def bench_ensemble(args, world, rank, local):
             extra["e2e_device_resident"] = device_resident_extras(eng, x0, v0, m32, dtype, inter_step)
             extra["simulator_api_N200_400_steps"] = simulator_api_extras(local, numba_api_ms)
             extra["e2e_positions_velocities_only"] = e2e_fields_extras(x0, v0, m32, dtype, local, inter_step)
+            if not args.no_cpu:
+                # the large-N CPU figure beside the single-system GPU rates above (flat in N: BASELINE.md section 2)
+                extra["reference_numba_force_eval_all_cores"] = numba_force_eval_extras()
         del outs
         torch.cuda.empty_cache()
         extra.update(sharded_extras(eng, world, rank, local))           # every rank takes part
