@@ -305,7 +305,9 @@ class NBodySimulator:
 
     def _aliased(self) -> bool:
         """Does anybody but this object hold a reference to the position / velocity host arrays (or a view of
-        them)?  Such an alias must see every step's in-place update, and may be written through at any time."""
+        them)?  Such an alias must see every step's in-place update, and may be written through at any time.
+        CPython reference counts against a baseline measured at import; anything that holds extra references (a
+        debugger, a tracer) only errs towards 'aliased', i.e. towards the reference's eager behaviour."""
         h = self._host
         return _refs(h, "positions") > _UNSHARED_REFS or _refs(h, "velocities") > _UNSHARED_REFS
 
