@@ -488,44 +488,34 @@ def test_interval_schedule_with_another_tenant_on_the_gpu(engine):
 
 @pytest.mark.parametrize("n,dtype,steps,every", [(700, "float64", 5, 1), (1000, "float32", 4, 2), (4099, "float32", 7, 3),
                                                  (4096, "float64", 3, 1), (16384, "float32", 6, 6), (9000, "float64", 2, 1),
-                                                 (20000, "float32", 3, 1), (32768, "float32", 2, 2)])
-def test_one_launch_run_bitwise_equals_per_step_launches(engine, monkeypatch, n, dtype, steps, every):
-    """K2p (csrc/nb_persist.cu, opt-in with NB_PERSIST=1: all steps of a run in ONE cooperative launch, warp-tasks on a
-    persistent grid, one grid barrier per step) against K2 (one launch per step, the default): the final state and
-    every snapshot row must be the same BITS -- same segment plan, same inner loops, same epilogue arithmetic."""
+                                                 (18000, "float32", 3, 1), (20000, "float32", 3, 1), (32768, "float32", 2, 2),
+                                                 (33, "float64", 4, 1), (641, "float32", 5, 5)])
+def test_step_kernel_variants_are_bit_identical(engine, monkeypatch, n, dtype, steps, every):
+    """The three ways a whole system is stepped on one GPU give the same BITS -- same segment plan, same inner loops,
+    same epilogue arithmetic: K2s (csrc/nb_group.cu, the default up to ~18,900 bodies: one CTA per group of bodies,
+    segment partials reduced in shared memory), K2 (nb_force.cu: (i-tile x segment) grid, partials reduced by the
+    last CTA of a tile; NB_NO_GROUP=1 -- what i-slabs and larger systems always use) and K2p (nb_persist.cu, opt-in
+    NB_PERSIST=1: all steps in one cooperative launch).  Final state, every snapshot row, and the accelerations of a
+    plain force evaluation."""
     import torch
     from hpc import ics
     from hpc.sharded import ShardedSystem
     x, v, m = ics.plummer_ic(n, seed=13)
     res = {}
-    for mode in ("persist", "per_step"):
-        if mode == "persist":
-            monkeypatch.setenv("NB_PERSIST", "1")
-        else:
-            monkeypatch.delenv("NB_PERSIST", raising=False)
+    for mode, env in (("group", {}), ("tiles", {"NB_NO_GROUP": "1"}), ("persist", {"NB_NO_GROUP": "1", "NB_PERSIST": "1"})):
+        for key in ("NB_NO_GROUP", "NB_PERSIST"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
         s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=np.dtype(dtype), device=engine.device)
+        a0 = s.acc.clone()
         n_snap = 1 + steps // every
         snaps = tuple(torch.zeros((n_snap, n, 3), dtype=torch.float64, device=engine.device) for _ in range(3))
         s.advance(steps, *snaps, save_interval=every)
         s.advance(2)                                   # a second call continues from the state the first left
         engine.step_status(s.ws, n)
-        res[mode] = (s.cur[:engine.padded_bodies(n) * 4].clone(), s.vel.clone(), s.acc.clone()) + tuple(t.clone() for t in snaps)
-    for a, b in zip(res["persist"], res["per_step"]):
-        assert torch.equal(a, b)
-    assert torch.isfinite(res["persist"][0]).all() and (res["persist"][3][1:] != 0).any()
-
-
-def test_ensemble_deferred_fields(engine):
-    """fields=(...) ships only the named snapshot stacks with the run; the others stay in HBM until first read."""
-    from hpc import ics
-    from hpc.ensemble import simulate_ensemble
-    x0, v0, m32 = ics.datagen_ensemble_ic(5, 200, seed=3)
-    full = simulate_ensemble(x0, v0, m32, dt=1e-3, n_steps=9, save_interval=3)
-    part = simulate_ensemble(x0, v0, m32, dt=1e-3, n_steps=9, save_interval=3, fields=("positions", "velocities"))
-    assert part.deferred() == ("accelerations",) and "accelerations" in part and len(part) == len(full)
-    assert np.array_equal(part["positions"], full["positions"]) and np.array_equal(part["velocities"], full["velocities"])
-    acc = part["accelerations"]                                  # first read: the device -> host copy happens now
-    assert part.deferred() == () and np.array_equal(acc, full["accelerations"]) and part["accelerations"] is acc
-    assert np.array_equal(part["times"], full["times"])
-    with pytest.raises(ValueError):
-        simulate_ensemble(x0, v0, m32, n_steps=2, fields=("momenta",))
+        res[mode] = (a0, s.cur[:engine.padded_bodies(n) * 4].clone(), s.vel.clone(), s.acc.clone()) + tuple(t.clone() for t in snaps)
+    for mode in ("tiles", "persist"):
+        for a, b in zip(res["group"], res[mode]):
+            assert torch.equal(a, b), mode
+    assert torch.isfinite(res["group"][1]).all() and (res["group"][4][1:] != 0).any()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Mid-size single systems, leapfrog step time: the one-launch kernel (K2p, nb_persist.cu) against one launch per step
-(K2, the default; K2p is opt-in with NB_PERSIST=1); ms per step, interactions/s, fraction of the 20-flop pipe peak."""
+"""Mid-size single systems, leapfrog step time of the three step kernels: K2s "group" (nb_group.cu: one CTA per group
+of bodies, shared-memory reduction; the default where the groups fit one wave), K2 "tiles" (nb_force.cu, NB_NO_GROUP=1)
+and K2p "one_launch" (nb_persist.cu, NB_PERSIST=1); us per step, interactions/s, fraction of the 20-flop pipe peak."""
 import json
 import os
 import sys
@@ -15,17 +16,19 @@ from hpc import _cuda, ics  # noqa: E402
 from hpc.sharded import ShardedSystem  # noqa: E402
 
 eng = _cuda.get_engine()
-sizes = [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096, 8192, 16384, 32768]
+sizes = [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096, 8192, 12288, 16384, 18000, 32768]
 for dtype, lanes in ((np.float32, 128), (np.float64, 64)):
     peak = eng.sm_count * lanes * 2 * 1.965e9 / 20.0
     for n in sizes:
         x, v, m = ics.plummer_ic(n, seed=7)
         row = {"n": n, "dtype": np.dtype(dtype).name}
-        for mode in ("one_launch", "per_step"):
+        for mode in ("group", "tiles", "one_launch"):
+            for key in ("NB_PERSIST", "NB_NO_GROUP"):
+                os.environ.pop(key, None)
+            if mode != "group":
+                os.environ["NB_NO_GROUP"] = "1"      # K2: (i-tile x segment) grid, one launch per step
             if mode == "one_launch":
-                os.environ["NB_PERSIST"] = "1"
-            else:
-                os.environ.pop("NB_PERSIST", None)
+                os.environ["NB_PERSIST"] = "1"       # K2p: all steps in one cooperative launch
             s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=dtype, device=0)
             steps = max(10, min(400, int(2e12 / (n * float(n)))))
             s.advance(steps)
