@@ -828,8 +828,27 @@ def single_system_extras(eng) -> dict:
                                             "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / peak_tf, 4),
                                             "peak_tflops": round(peak_tf, 2)}
     del stream, ws
-    # the metric's other size, N = 1,048,576 (config 5), float32: two full leapfrog steps on this one GPU
+    # mid-size single systems (configs[2] is N = 16,384): leapfrog steps through the resident-state path.  N <= 9,472
+    # takes K2s (one CTA per group of bodies, no cross-CTA reduction), larger systems K2 (i-tile x segment grid)
     from hpc.sharded import ShardedSystem
+    for n in (4096, 16384):
+        x, v, m = ics.plummer_ic(n, seed=7)
+        for tag, dtype, lanes in (("f32", np.float32, 128), ("f64", np.float64, 64)):
+            sysm = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=dtype, device=eng.device)
+            steps = 200 if n <= 4096 else 50
+            sysm.advance(steps)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sysm.advance(steps)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) / steps * 1e3
+            gi = n * (n - 1.0) / us / 1e3
+            peak_tf = eng.sm_count * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+            out[f"single_system_N{n}_{tag}_leapfrog"] = {"us_per_step": round(us, 2), "Ginteractions_per_s": round(gi, 1),
+                                                         "frac_of_pipe_peak_20flop": round(gi * 1e9 * 20 / 1e12 / peak_tf, 4)}
+            del sysm
+    # the metric's other size, N = 1,048,576 (config 5), float32: two full leapfrog steps on this one GPU
     n = 1 << 20
     x, v, m = ics.plummer_ic(n, seed=7)
     sysm = ShardedSystem(x, v, m, dt=1e-3, softening=1e-3, dtype=np.float32, device=eng.device)

@@ -159,7 +159,10 @@ int nb_step_status(const void* workspace, int n, nb_stream_t s);
  * (v_0, a_0) on entry and (v_n, a_n) on return.  Snapshot s (s = 1..n_steps/save_interval) of the
  * state after step s*save_interval goes to row block s of snap_* ((n_snap, n, 3) float64, n_snap =
  * 1 + n_steps/save_interval); row block 0 (the initial state) is written here too. */
-/* Opt-in, environment NB_PERSIST=1: systems of at most nb_persist_max_bodies() bodies run ALL their steps in one
+/* Whole systems (i0 == 0, n_i == n) of at most 64 bodies per SM run nb_accel_* / nb_step_* / nb_run_* through K2s
+ * (csrc/nb_group.cu: one thread block per group of bodies, the segment partials reduced in shared memory) -- the same
+ * bits as the (i-tile x segment) kernels, which environment NB_NO_GROUP=1 selects for them too.
+ * Opt-in, environment NB_PERSIST=1: systems of at most nb_persist_max_bodies() bodies run ALL their steps in one
  * cooperative launch (K2p, csrc/nb_persist.cu: warp-tasks on a persistent grid, one grid barrier per step) --
  * bit-identical to the per-step launches and, as measured, no faster; nb_step_status(workspace) reports
  * a stalled launch. */

@@ -563,11 +563,11 @@ static int force_pass(const T* stream, const Slab& sl, double softening, T* part
 
 // Whole systems small enough for one wave of group CTAs take K2s (nb_group.cu: no cross-CTA reduction, the same bits);
 // NB_NO_GROUP=1 keeps K2 (the tests compare the two).
-static int whole_system_kp(const Slab& sl) {
+static int whole_system_kp(const Slab& sl, int is_f64) {
     if (sl.i0 != 0 || sl.n_i != sl.n) return 0;
     const char* e = getenv("NB_NO_GROUP");
     if (e && e[0] == '1') return 0;
-    return group_step_kp(sl.n, sl.n_seg, sm_count());
+    return group_step_kp(sl.n, sl.n_seg, sm_count(), is_f64);
 }
 
 template <typename T>
@@ -578,7 +578,7 @@ static int accel_impl(const T* stream, int n, int i0, int n_i, double softening,
     NB_REQUIRE(stream && acc && ws, "null pointer argument");
     NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
                nb_workspace_bytes(n, n_i, sizeof(T) == 8));
-    if (const int kp = whole_system_kp(sl))
+    if (const int kp = whole_system_kp(sl, sizeof(T) == 8))
         return group_step<T>(stream, nullptr, nullptr, acc, n, 0.0, softening, /*mode=*/1, 0, nullptr, nullptr, nullptr,
                              error_word(ws, n), kp, st);
     T* partial = partials<T>(ws, n);
@@ -598,7 +598,7 @@ static int step_impl(const T* cur, T* next, T* vel, T* acc, int n, int i0, int n
     NB_REQUIRE(!(flags & NB_STEP_CONTINUE) || next, "NB_STEP_CONTINUE needs stream_next");
     NB_REQUIRE(ws_bytes >= nb_workspace_bytes(n, n_i, sizeof(T) == 8), "workspace too small: %zu < %zu", ws_bytes,
                nb_workspace_bytes(n, n_i, sizeof(T) == 8));
-    if (const int kp = whole_system_kp(sl))
+    if (const int kp = whole_system_kp(sl, sizeof(T) == 8))
         return group_step<T>(cur, next, vel, acc, n, dt, softening, /*mode=*/2, flags, sp, sv, sa, error_word(ws, n), kp,
                              st);
     T* partial = partials<T>(ws, n);

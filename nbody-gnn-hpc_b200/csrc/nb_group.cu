@@ -1,5 +1,5 @@
-// nb_group.cu -- K2s: the force pass + leapfrog of one step for systems of up to a few thousand bodies per SM
-// (640 < N <= ~18,000 on 148 SMs), ONE CTA PER GROUP OF BODIES, no cross-CTA reduction (sm_100a).
+// nb_group.cu -- K2s: the force pass + leapfrog of one step for whole systems of up to 64 bodies per SM (N <= 9,472 on
+// 148 SMs), ONE CTA PER GROUP OF BODIES, no cross-CTA reduction (sm_100a).
 //
 // Replaces NBodySimulator.step, reference src/hpc/nbody.py:202-218, in the size range where K2 (nb_force.cu) spends
 // most of a step on a chain of L2 round trips: there a body's j-segments are summed by DIFFERENT CTAs, so every step
@@ -12,8 +12,8 @@
 // the body -- closing kick, snapshot row, next opening kick, drift into the other stream buffer -- with the arithmetic
 // of K2's epilogue: the same bits as K2 for every body, step after step (tested), hence still bit-identical to any
 // i-slab / rank decomposition that uses K2.  One launch per step, chained by programmatic dependent launch like K2.
-// kP (1, 2 or 4) is the smallest for which the groups fit the SMs in one wave; systems that need more than one
-// wave even at kP = 4 stay with K2, whose (i-tile x segment) grid fills the machine better.
+// kP (1 or 2) is the smallest for which the groups fit the SMs in one wave (N <= 64 x SMs = 9,472 on a B200); larger
+// systems stay with K2, whose (i-tile x segment) grid fills the machine better.
 #include "nb_warptask.cuh"
 
 namespace nb {
@@ -97,11 +97,17 @@ __global__ void __launch_bounds__(kGroupMaxWarps * 32, 1) group_step_kernel(cons
     }
 }
 
-// The smallest kP in {1, 2, 4} whose groups fit the SMs in one wave; 0: this system is K2's.
-int group_step_kp(int n, int n_seg, int sms) {
+// The smallest kP in {1, 2} whose groups fit the SMs in one wave; 0: this system is K2's.  (kP = 4 would take systems
+// up to 18,944 bodies, but its 96 .. 148 CTAs of 16 warps fill the machine worse than K2's grid does: measured 94.9 us
+// against 77.8 us per step at N = 12,288 and 124 against 116 at 16,384, profiles/r02_midn_group.log.)
+// In float64 kP = 2 is taken only when its groups fill at least 80 % of the SMs: below that K2 is faster (N = 5,000:
+// 79 groups, 53.4 us against 41.6 us per step; from N ~ 7,600 up K2s wins again, 95 against 113 us at 9,472); in
+// float32 K2s is at least as fast as K2 over the whole range (profiles/r02_midn_group.log).
+int group_step_kp(int n, int n_seg, int sms, int is_f64) {
     if (n_seg < 1 || n_seg > kGroupMaxWarps) return 0;
-    for (int kp : {1, 2, 4})
-        if (ceil_div(n, 32 * kp) <= sms) return kp;
+    if (ceil_div(n, 32) <= sms) return 1;
+    const int groups2 = ceil_div(n, 64);
+    if (groups2 <= sms && (!is_f64 || groups2 * 10 >= sms * 8)) return 2;
     return 0;
 }
 
@@ -118,14 +124,13 @@ int group_step(const T* cur, T* next, T* vel, T* acc, int n, double dt, double s
     g.sp = sp; g.sv = sv; g.sa = sa; g.error = error;
     const bool zero = !(g.eps2 > T(0));
     void (*kern)(const GroupArgs<T>);
-    if (kP == 4) kern = zero ? group_step_kernel<T, 4, true> : group_step_kernel<T, 4, false>;
-    else if (kP == 2) kern = zero ? group_step_kernel<T, 2, true> : group_step_kernel<T, 2, false>;
+    if (kP == 2) kern = zero ? group_step_kernel<T, 2, true> : group_step_kernel<T, 2, false>;
     else kern = zero ? group_step_kernel<T, 1, true> : group_step_kernel<T, 1, false>;
     const size_t smem = (size_t)g.n_seg * (kPStages * (kPTileBytes + sizeof(uint64_t)) + 3 * 32 * kP * sizeof(T));
-    static bool attr_set[2][3][2] = {};
-    bool& done = attr_set[sizeof(T) == 8][kP == 4 ? 2 : kP - 1][zero];
+    static bool attr_set[2][2][2] = {};
+    bool& done = attr_set[sizeof(T) == 8][kP - 1][zero];
     if (!done) {  // the permission for the largest shape, once per kernel
-        const size_t smem_max = (size_t)kGroupMaxWarps * (kPStages * (kPTileBytes + sizeof(uint64_t)) + 3 * 32 * 4 * sizeof(double));
+        const size_t smem_max = (size_t)kGroupMaxWarps * (kPStages * (kPTileBytes + sizeof(uint64_t)) + 3 * 32 * 2 * sizeof(double));
         NB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         done = true;
     }

@@ -102,7 +102,7 @@ int persist_run(T* stream_a, T* stream_b, T* vel, T* acc, int n, double dt, doub
 
 // nb_group.cu: one CTA per group of bodies, segment partials reduced in shared memory (whole systems that fit the
 // SMs in one wave); group_step_kp() says whether a system qualifies (0: no) and with how many bodies per lane
-int group_step_kp(int n, int n_seg, int sms);
+int group_step_kp(int n, int n_seg, int sms, int is_f64);
 template <typename T>
 int group_step(const T* cur, T* next, T* vel, T* acc, int n, double dt, double softening, int mode, int flags,
                double* sp, double* sv, double* sa, int* error, int kP, cudaStream_t st);
