@@ -94,6 +94,16 @@ if "peer" in which:
         cur, nxt = nxt, cur
     torch.cuda.synchronize()
     eng.step_status(ws, n)
+if "group" in which:
+    # K2s: whole mid-size systems, one CTA per group of bodies (N = 4,096 and 8,192, both precisions, five steps each)
+    from hpc.sharded import ShardedSystem
+    for n in (4096, 8192):
+        x, v, m = ics.plummer_ic(n, seed=7)
+        for dtype in (np.float32, np.float64):
+            s = ShardedSystem(x, v, m, dt=1e-3, softening=0.01, dtype=dtype, device=0)
+            for _ in range(2):
+                s.advance(5)
+            torch.cuda.synchronize()
 if "persist" in which:
     # K2p (opt-in): ten leapfrog steps of N = 16,384 in one cooperative launch, both precisions
     import os
