@@ -716,6 +716,20 @@ def simulator_api_extras(local: int, numba_api_ms) -> dict:
            "step_loop_us_per_step": round(best["step_loop"] * 1e6 / ENS_STEPS, 2)}
     if numba_api_ms is not None:
         out["reference_numba_1_thread"] = {"run_400_ms": round(numba_api_ms[0], 2), "step_loop_400_ms": round(numba_api_ms[1], 2)}
+    # the reference's own timing script, scripts/benchmark_bh_temp.py:19-34: NBodySimulator(n_particles=5000,
+    # use_barnes_hut=True), one warm-up step, then timed sim.step() calls (there: a theta = 0.5 tree walk on one core;
+    # here: the exact direct sum, state resident on the GPU)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = NBodySimulator(n_particles=5000, use_barnes_hut=True, seed=1, device=local)
+    sim.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        sim.step()
+    torch.cuda.synchronize()
+    out["benchmark_bh_temp_N5000_us_per_step"] = round((time.perf_counter() - t0) / 50 * 1e6, 1)
     return out
 
 
