@@ -208,6 +208,23 @@ int nb_ensemble_f32(double* x, double* v, double* a, const void* masses, int mas
                     double* out_x, double* out_v, double* out_a, int n_snap_total, int snap_offset,
                     void* workspace, size_t workspace_bytes, nb_stream_t s);
 
+/* Ensembles of systems too large for one CTA's shared memory (N > nb_ensemble_max_bodies(), up to
+ * nb_batched_max_bodies()): the same per-simulation work of generate_data.py:32-58 -- which the unchanged script asks
+ * for with --particles in the thousands -- B systems side by side in every launch (K2s, csrc/nb_group.cu, grid =
+ * groups x B), one launch per leapfrog step for the whole ensemble instead of one run per system.
+ *   streams     (B, nb_stream_elems(n)) stream layout, one system after the other (nb_pack_* per system)
+ *   vel, acc    (B, n, 3) in the kernel dtype; snap_*  (B, 1 + n_steps/save_interval, n, 3) float64 or all NULL
+ * nb_accel_batched_*: a_0 of every system.  nb_run_batched_*: the run loop, as nb_run_* for one system. */
+int nb_batched_max_bodies(void);
+int nb_accel_batched_f64(const double* streams, int B, int n, double softening, double* acc, nb_stream_t s);
+int nb_accel_batched_f32(const float* streams, int B, int n, double softening, float* acc, nb_stream_t s);
+int nb_run_batched_f64(double* stream_a, double* stream_b, double* vel, double* acc, int B, int n, double dt,
+                       double softening, int n_steps, int save_interval,
+                       double* snap_pos, double* snap_vel, double* snap_acc, int* final_in_a, nb_stream_t s);
+int nb_run_batched_f32(float* stream_a, float* stream_b, float* vel, float* acc, int B, int n, double dt,
+                       double softening, int n_steps, int save_interval,
+                       double* snap_pos, double* snap_vel, double* snap_acc, int* final_in_a, nb_stream_t s);
+
 /* Strided device -> host copy of snapshot rows (height rows of width bytes; pitches in bytes), so the
  * rows of one step-chunk of every system can drain to pinned host memory while the next chunk runs. */
 int nb_copy_rows_d2h_async(void* dst_host, size_t dpitch, const void* src_dev, size_t spitch, size_t width,

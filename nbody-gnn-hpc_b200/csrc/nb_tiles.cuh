@@ -105,6 +105,6 @@ int persist_run(T* stream_a, T* stream_b, T* vel, T* acc, int n, double dt, doub
 int group_step_kp(int n, int n_seg, int sms, int is_f64);
 template <typename T>
 int group_step(const T* cur, T* next, T* vel, T* acc, int n, double dt, double softening, int mode, int flags,
-               double* sp, double* sv, double* sa, int* error, int kP, cudaStream_t st);
+               double* sp, double* sv, double* sa, int* error, int kP, cudaStream_t st, int B = 1, size_t snap_stride = 0);
 
 }  // namespace nb

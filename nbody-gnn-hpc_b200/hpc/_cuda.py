@@ -86,6 +86,11 @@ _SIGNATURES = {
                               _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
     "nb_ensemble_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _cd, _ci, _ci, _ci, _ci,
                               _vp, _vp, _vp, _ci, _ci, _vp, _sz, _vp]),
+    "nb_batched_max_bodies": (_ci, []),
+    "nb_accel_batched_f64": (_ci, [_vp, _ci, _ci, _cd, _vp, _vp]),
+    "nb_accel_batched_f32": (_ci, [_vp, _ci, _ci, _cd, _vp, _vp]),
+    "nb_run_batched_f64": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _ip, _vp]),
+    "nb_run_batched_f32": (_ci, [_vp, _vp, _vp, _vp, _ci, _ci, _cd, _cd, _ci, _ci, _vp, _vp, _vp, _ip, _vp]),
     "nb_copy_rows_d2h_async": (_ci, [_vp, _sz, _vp, _sz, _sz, _sz, _vp]),
     "nb_energy_workspace_bytes": (_sz, [_ci, _ci]),
     "nb_energy_f64": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _cd, _vp, _vp, _sz, _vp]),
@@ -560,6 +565,10 @@ class Engine:
             raise ValueError(f"masses must be (N,) or (B,N); got {m.shape}")
         if outputs not in ("host", "device"):
             raise ValueError("outputs must be 'host' or 'device'")
+        if int(self.lib.nb_ensemble_max_bodies()) < N <= int(self.lib.nb_batched_max_bodies()):
+            # systems too large for one CTA's shared memory: all B side by side in every launch (K2s, grid = groups x B)
+            return self._ensemble_batched(x0, v0, m, mass_stride, dt, softening, n_steps, save_interval, dtype, a0,
+                                          snapshots, outputs)
         if N > int(self.lib.nb_ensemble_max_bodies()):
             if outputs == "device":
                 raise NotImplementedError("device-resident outputs need systems that fit one CTA's shared memory "
@@ -648,6 +657,48 @@ class Engine:
                     res[name] = host_t.numpy()
                 else:
                     res.defer(name, lambda t=dev_t: self.to_host(t))     # keeps the device stack alive until read
+            return res
+
+    def _ensemble_batched(self, x0, v0, m, mass_stride, dt, softening, n_steps, save_interval, dtype, a0, snapshots,
+                          outputs) -> dict:
+        """Engine.ensemble for nb_ensemble_max_bodies() < N <= nb_batched_max_bodies(): one batched launch per step."""
+        torch = _torch()
+        B, N = x0.shape[0], x0.shape[1]
+        sfx, td = self._suffix(dtype), self._tdtype(dtype)
+        n_snap = 1 + n_steps // save_interval
+        with torch.cuda.device(self.device):
+            x_d = self.to_device(x0)                                           # (B, N, 3) float64
+            m_d, f32 = self._masses_dev(np.ascontiguousarray(m))
+            elems = self.stream_elems(N, dtype) if hasattr(self, "stream_elems") else self.padded_bodies(N) * 4
+            sa = torch.empty((B, elems), dtype=td, device=self.device)
+            for b in range(B):                                                  # layout change, once per run
+                self.pack(x_d[b], m_d if mass_stride == 0 else m_d[b], f32, N, dtype, out=sa[b])
+            sb = sa.clone()
+            vel = self.to_device(v0, td).contiguous()
+            if a0 is None:
+                acc = torch.empty((B, N, 3), dtype=td, device=self.device)
+                self._check(getattr(self.lib, f"nb_accel_batched_{sfx}")(self._p(sa), B, N, float(softening),
+                                                                        self._p(acc), self._stream()))
+                self.launches += 1
+            else:
+                acc = self.to_device(np.ascontiguousarray(a0, dtype=np.float64), td).contiguous()
+            snaps = (torch.empty((3, B, n_snap, N, 3), dtype=torch.float64, device=self.device) if snapshots else None)
+            fin = ctypes.c_int(1)
+            self._check(getattr(self.lib, f"nb_run_batched_{sfx}")(
+                self._p(sa), self._p(sb), self._p(vel), self._p(acc), B, N, float(dt), float(softening), int(n_steps),
+                int(save_interval), self._p(snaps[0] if snapshots else None), self._p(snaps[1] if snapshots else None),
+                self._p(snaps[2] if snapshots else None), fin, self._stream()))
+            self.launches += (2 if snapshots else 1) + n_steps
+            cur = sa if fin.value else sb
+            final_pos = torch.stack([self.unpack(cur[b], N) for b in range(B)])
+            res = {"final_positions": self.to_host(final_pos), "final_velocities": self.to_host(vel),
+                   "final_accelerations": self.to_host(acc)}
+            if snapshots:
+                if outputs == "device":
+                    res.update(positions=snaps[0], velocities=snaps[1], accelerations=snaps[2])
+                else:
+                    res.update(positions=self.to_host(snaps[0]), velocities=self.to_host(snaps[1]),
+                               accelerations=self.to_host(snaps[2]))
             return res
 
     def _copy_stream(self):
