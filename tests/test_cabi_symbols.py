@@ -126,3 +126,11 @@ def test_bad_arguments_of_the_round2_entry_points():
     assert rc == 1 and b"workspace too small" in lib.nb_last_error()
     assert lib.nb_step_status(None, 64, None) == 1 and lib.nb_probe_occupy(0, 0, 1.0, None) == 1
     assert lib.nb_workspace_bytes(4096, 4096, 0) > lib.nb_workspace_bytes(4096, 2048, 0)   # whole-system workspaces carry K2p's words
+    # batched mid-size ensembles
+    assert lib.nb_batched_max_bodies() > lib.nb_ensemble_max_bodies()
+    assert lib.nb_accel_batched_f64(None, 2, 2000, 1e-9, buf, None) == 1 and b"nb_accel_batched" in lib.nb_last_error()
+    assert lib.nb_accel_batched_f32(buf, 2, 10 ** 6, 1e-9, buf, None) == 1                  # n beyond the batched limit
+    rc = lib.nb_run_batched_f64(buf, buf, buf, buf, 2, 2000, 1e-3, 1e-9, 4, 0, None, None, None, None, None)
+    assert rc == 1 and b"save_interval" in lib.nb_last_error()
+    rc = lib.nb_run_batched_f32(buf, buf, buf, buf, 2, 2000, 1e-3, 1e-9, 4, 1, buf, None, None, None, None)
+    assert rc == 1 and b"all set or all null" in lib.nb_last_error()
