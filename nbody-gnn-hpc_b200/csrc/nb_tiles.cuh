@@ -47,7 +47,10 @@ __device__ __forceinline__ void f32_pairs(const float4* __restrict__ t, int n_pa
                                           const float (&yi)[kP], const float (&zi)[kP], float2 (&ax)[kP],
                                           float2 (&ay)[kP], float2 (&az)[kP], float eps2) {
     const float2 e2 = make_float2(eps2, eps2);
-#pragma unroll 2
+    // j pairs in flight per thread: kP bodies already give kP independent chains per pair; one body per lane (the
+    // group-per-CTA kernel at N <= 4,736) needs more pairs in flight to fill the pipe
+    constexpr int kUnroll = kP == 1 ? 8 : 2;
+#pragma unroll kUnroll
     for (int jp = 0; jp < n_pairs; ++jp) {
         const float4 A = t[2 * jp];      // x0 x1 y0 y1
         const float4 B = t[2 * jp + 1];  // z0 z1 gm0 gm1
@@ -83,7 +86,8 @@ template <int kP, bool kZeroEps>
 __device__ __forceinline__ void f64_bodies(const double2* __restrict__ t, int n_j, const double (&xi)[kP],
                                            const double (&yi)[kP], const double (&zi)[kP], double (&ax)[kP],
                                            double (&ay)[kP], double (&az)[kP], double eps2) {
-#pragma unroll 4
+    constexpr int kUnroll = kP == 1 ? 8 : 4;
+#pragma unroll kUnroll
     for (int j = 0; j < n_j; ++j) {
         const double2 a = t[2 * j];      // x y
         const double2 b = t[2 * j + 1];  // z gm
