@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(kGroupMaxWarps * 32, 1) group_step_kernel(cons
     uint32_t tiles_done = 0;
     const bool ok = WarpTask<T, kP, kZeroEps>::run(cur, g.n, grp, j0, j1, g.eps2, part + (size_t)warp * 3 * kBodies,
                                                    kBodies, b0, ring, bars, tiles_done, lane);
-    if (!ok && lane == 0 && g.error) atomicCAS(g.error, 0, NB_PERSIST_STALLED);
+    if (!ok) {  // a tile copy never completed: never a silent wrong answer
+        if (g.error == nullptr) __trap();  // batched launches have no error word: the launch fails, the host sees it
+        if (lane == 0) atomicCAS(g.error, 0, NB_PERSIST_STALLED);
+    }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the successor's CTAs may be placed from here on
     __syncthreads();
 
